@@ -1,0 +1,190 @@
+/*
+ * r6dof.h — C ABI of libr6dof.so: the B200 (sm_100a) batched 6DOF rocket-landing env step.
+ *
+ * The reference (Tuxliri/RL_Rocket_6DOF) is pure Python and has no FFI seam; the boundary it
+ * offers is the gym API of `Rocket6DOF` (my_environment/envs/rocket_env.py:16-231) and, one level
+ * up, the stable-baselines3 VecEnv protocol that SB3 wraps around it (main_6DOF.py:105-114,
+ * montecarlo_script.py:54-64).  This header is what a ctypes binding of those two call sites
+ * binds: every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  Every buffer pointer is DEVICE memory owned
+ *    by the caller (a torch CUDA tensor's data_ptr()); the library allocates nothing and keeps
+ *    no global state except a thread-local error string.
+ *  - every call enqueues work on the caller's stream (`cudaStream_t` passed as void*) and returns
+ *    without synchronising; results are valid after the stream is synchronised.
+ *  - return value: 0 on success, negative R6_E* on error; r6_last_error() has the text.
+ *  - per-env arrays are structure-of-arrays, component-major: x[c][n]  (c*n + i).
+ *    Actions are the exception: [n][3] float32 row-major, exactly the array SB3 hands to
+ *    VecEnv.step_async.
+ *  - environments are independent; `env_offset` is the global index of local env 0 so that the
+ *    counter-based RNG gives the same streams whatever the shard count.
+ */
+#ifndef R6DOF_H
+#define R6DOF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R6_ABI_VERSION 3
+#define R6_NSTATE 14
+#define R6_NTERMS 7
+#define R6_NSTATS 8
+
+/* error codes */
+#define R6_OK 0
+#define R6_EINVAL (-1) /* bad argument (null pointer, n < 0, bad mode) */
+#define R6_ECUDA (-2)  /* CUDA launch / runtime error, text in r6_last_error() */
+
+/* flags[] bits written by step / rollout (rocket_env.py:213, 226, 382-390; main_6DOF.py:47-50) */
+#define R6_F_EVENT 0x01      /* solve_ivp status != 0 (ground event or solver failure) */
+#define R6_F_OOB 0x02        /* _check_bounds_violation */
+#define R6_F_TRUNCATED 0x04  /* TimeLimit hit and not done ("TimeLimit.truncated") */
+#define R6_F_ZERO_HEIGHT 0x08
+#define R6_F_VEL_LIMIT 0x10
+#define R6_F_LAND_RADIUS 0x20
+#define R6_F_ATT_LIMIT 0x40
+#define R6_F_OMEGA_LIMIT 0x80
+#define R6_F_LANDING_ALL 0xF8
+
+/* stats[] slots (device accumulators, float64; reduced over ranks with one all_reduce(SUM)) */
+enum {
+    R6_S_EPISODES = 0, R6_S_RETURN_SUM, R6_S_LENGTH_SUM, R6_S_LANDED,
+    R6_S_GROUND, R6_S_OOB, R6_S_TRUNCATED, R6_S_STEPS
+};
+
+/* action sources of r6_rollout */
+#define R6_ACT_PHILOX 0  /* uniform(-1,1) float32 from Philox4x32-10 (synthetic random policy) */
+#define R6_ACT_MLP 1     /* deterministic SB3 MlpPolicy forward, fused (montecarlo_script.py:57-64) */
+#define R6_ACT_BUFFER 2  /* actions read from a [k][n][3] device buffer */
+
+/*
+ * Derived constants of Rocket6DOF.__init__ (rocket_env.py:71-134, 159-168), the wrappers of
+ * make_env() (main_6DOF.py:33-53) and the simulator (simulator.py:9-67).  The host computes them
+ * with the reference's own numpy expressions (rl_rocket_6dof_b200/params.py) so that NumPy-version
+ * promotion rules never enter the kernel.  Layout is checked at load time with r6_params_size().
+ */
+typedef struct R6Params {
+    double dt;                 /* timestep */
+    double max_gimbal;         /* np.deg2rad(20) */
+    double normalizer[R6_NSTATE];
+    double alfa, eta, gamma, kappa;
+    double att_traj_limit[3];  /* rad */
+    double land_att_limit[3];  /* rad */
+    double omega_lim[3];
+    double waypoint;
+    double clip_lo, clip_hi;   /* ClipReward bounds (used when clip_reward != 0) */
+    double oob_penalty;        /* -50, rocket_env.py:228-229 */
+    float max_thrust;
+    float beta, w_v_f, w_r_f, max_r_f, max_v_f;
+    float maximum_v, target_r, zero_height_tol;
+    float bounds_low[3], bounds_high[3];
+    float ic_low[R6_NSTATE], ic_high[R6_NSTATE];
+    int32_t shaping_velocity;   /* 0 'acceleration', 1 'velocity' */
+    int32_t max_episode_steps;  /* TimeLimit; 0 = none */
+    int32_t clip_reward;        /* apply ClipReward(clip_lo, clip_hi) to reward[] */
+    int32_t auto_reset;         /* VecEnv semantics: reset finished envs inside the step */
+    int32_t n_t;                /* entries in R6Buffers.t_table */
+    int32_t reserved;
+} R6Params;
+
+/* Device pointers. n = number of local envs. Nullable members are marked. */
+typedef struct R6Buffers {
+    /* persistent env state */
+    double *state;          /* [14][n] float64 (Simulator6DOF.state) */
+    float *m0;              /* [n] initial mass of the episode (simulator.py:42) */
+    float *v0;              /* [n] ||IC[3:6]|| (rocket_env.py:651) */
+    int32_t *step_count;    /* [n] steps taken in the episode (time = t_table[step_count]) */
+    uint32_t *episode_id;   /* [n] episodes started by this env (RNG counter) */
+    double *ep_return;      /* [n] running sum of reward[] over the episode (Monitor "r") */
+    /* per-step outputs */
+    float *obs;             /* [14][n] (row 13 = mass/normalizer; RemoveMassFromObs = rows 0..12) */
+    double *reward;         /* [n] */
+    uint8_t *done;          /* [n] done OR truncated (what a VecEnv reports) */
+    uint8_t *flags;         /* [n] R6_F_* */
+    float *terminal_obs;    /* [14][n] obs of the last step of a finished episode ("terminal_observation") */
+    double *terminal_state; /* [14][n] SIM.states[-1] of a finished episode (montecarlo_script.py:35) */
+    double *reward_terms;   /* [7][n] nullable: rewards_dict values in insertion order */
+    uint8_t *nattempts;     /* [n] nullable: RK attempts of the step (nfev = 2 + 6*nattempts) */
+    int8_t *status;         /* [n] nullable: solve_ivp status of the step (0, 1, -1) */
+    float *ep_info;         /* [2][n] nullable: (return, length) of the episode that just finished */
+    /* tables */
+    const double *t_table;  /* [n_t] t_k = round(t_{k-1}+dt, 3) (simulator.py:92) */
+    const float *ic_table;  /* [ic_table_len][14] nullable: initial conditions to replay instead of
+                               sampling; row = (global_env + n_global*episode) % ic_table_len */
+    int64_t ic_table_len;
+    int64_t n_global;       /* total envs over all shards (ic_table indexing) */
+    double *stats;          /* [8] nullable: R6_S_* accumulators */
+} R6Buffers;
+
+/* Weights of the SB3 MlpPolicy actor (net_arch [128, 64], tanh), float32 row-major [out][in]. */
+typedef struct R6Mlp {
+    const float *w0, *b0;   /* [128][13], [128] */
+    const float *w1, *b1;   /* [64][128], [64]  */
+    const float *w2, *b2;   /* [3][64],  [3]    */
+} R6Mlp;
+
+int r6_abi_version(void);
+const char *r6_last_error(void);
+int r6_params_size(void);
+int r6_buffers_size(void);
+
+/*
+ * Rocket6DOF.reset (rocket_env.py:180-199) + Simulator6DOF.__init__ (simulator.py:9-67) for every
+ * env whose mask byte is non-zero (mask == NULL: all).  Initial conditions are drawn uniformly in
+ * [ic_low, ic_high] in float64 and cast to float32 like gym's Box.sample, then the quaternion is
+ * normalised in float32 (rocket_env.py:190).  RNG: Philox4x32-10, key = seed,
+ * counter = (global env id, episode id).  Writes state, m0, v0, step_count = 0, ep_return = 0, obs.
+ */
+int r6_reset(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset,
+             const uint8_t *mask, uint64_t seed, void *stream);
+
+/*
+ * Rocket6DOF.step (rocket_env.py:201-231) through Simulator6DOF.step (simulator.py:69-104) and
+ * SciPy's solve_ivp/RK45, with the make_env() wrappers (RemoveMassFromObs is a view of obs,
+ * ClipReward, TimeLimit) and the DummyVecEnv auto-reset when p->auto_reset is set.
+ * actions: [n][3] float32 in [-1, 1].
+ */
+int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset,
+            const float *actions, uint64_t seed, void *stream);
+
+/*
+ * k fused env-steps per launch with the state held in registers (auto-reset always on).
+ * mode R6_ACT_PHILOX: action = uniform(-1,1) from (seed, global env id, step_base + j);
+ * mode R6_ACT_MLP:    action = clip(actor(obs[0:13]), -1, 1) (evaluate_policy, deterministic);
+ * mode R6_ACT_BUFFER: action = act_buf[j][i][:].
+ * traj_* (nullable) record the rollout: obs [k][13][n] (observation the action was computed
+ * from), act [k][n][3], rew [k][n] float32, done [k][n] uint8.
+ */
+int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, int32_t k,
+               int32_t mode, const R6Mlp *mlp, const float *act_buf, uint64_t seed,
+               int64_t step_base, float *traj_obs, float *traj_act, float *traj_rew,
+               uint8_t *traj_done, void *stream);
+
+/*
+ * Simulator6DOF.step in raw mode (python-list IC / control: everything float64),
+ * the call of test_6DOF_simulator.py:3-7.  state [14][n] in/out, u [3][n], m0 [n], t [n],
+ * status [n] out, nattempts [n] nullable.
+ */
+int r6_sim_step_raw(double *state, const double *u, const double *m0, const double *t, double dt,
+                    int64_t n, int8_t *status, uint8_t *nattempts, void *stream);
+
+/* _compute_atarg's t_go (rocket_env.py:528-546): largest positive real root of
+ * c0 t^4 + c2 t^2 + c3 t + c4, one per element (NaN when there is none). */
+int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo,
+           void *stream);
+
+/* Zeroes stats[8] (asynchronously, on the stream). */
+int r6_stats_reset(double *stats, void *stream);
+
+/* Micro-benchmarks for the roofline denominators: a dependent-free DFMA / FFMA
+ * loop; returns nothing, the caller times it.  flops = 2 * threads * iters * 8 chains. */
+int r6_peak_fma(int32_t fp64, int64_t blocks, int32_t iters, double *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R6DOF_H */
