@@ -1,0 +1,986 @@
+// r6_core.cuh — per-environment math of the batched 6DOF env step (one thread = one environment).
+//
+// Restates, B200-first, the hot path of Tuxliri/RL_Rocket_6DOF:
+//   Rocket6DOF.step            my_environment/envs/rocket_env.py:201-231
+//   Simulator6DOF.step / RHS   my_environment/utils/simulator.py:69-143
+//   SciPy solve_ivp RK45       scipy/integrate/_ivp/rk.py:14-180, common.py:63-134, ivp.py:52-158,646-716
+//   reward / flags / obs       rocket_env.py:317-402, 503-566, 591-617
+// following the verified precision map of SURVEY.md Appendix A (float32 where the reference is
+// float32, float64 elsewhere).  It is NOT a transliteration: the right-hand side is algebraically
+// de-duplicated (one rotation matrix, un-normalised quaternion scaled by 1/|q|^2, gyroscopic term
+// of the axisymmetric body folded), the position rows of the Runge–Kutta stages are eliminated with
+// the squared tableau (A·A, Bᵀ·A, Eᵀ·A) so a stage stores 9 instead of 14 doubles, the air density is
+// expanded around the step's initial height, and the Euler-angle limit tests are done on cosines
+// instead of atan2.  All of these change results at the 1e-16 level only (tolerance is 1e-9).
+//
+// The file compiles for the device (nvcc, sm_100a) and — for tests/hostsim only — for the host with
+// g++ (R6_HOST_BUILD).  The product never uses the host build.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/r6dof.h"
+
+#if defined(__CUDACC__)
+#define R6_HD __host__ __device__ __forceinline__
+#define R6_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define R6_HD inline
+#define R6_HD_NOINLINE
+#endif
+
+namespace r6 {
+
+// ------------------------------------------------------------------------------------------------
+// float32 primitives that must not be contracted / reassociated
+#if defined(__CUDA_ARCH__)
+R6_HD float f32_mul(float a, float b) { return __fmul_rn(a, b); }
+R6_HD float f32_add(float a, float b) { return __fadd_rn(a, b); }
+R6_HD float f32_sub(float a, float b) { return __fsub_rn(a, b); }
+R6_HD float f32_div(float a, float b) { return __fdiv_rn(a, b); }
+R6_HD float f32_sqrt(float a) { return __fsqrt_rn(a); }
+R6_HD float f32_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+R6_HD float f64_to_f32(double a) { return __double2float_rn(a); }
+// fast reciprocal / rsqrt: MUFU seed (2^-23) + two Newton steps => <= ~2 ulp, no IEEE special cases.
+R6_HD double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+R6_HD double fast_sqrt(double x)
+{
+    if (x == 0.0) return 0.0;
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    // Newton on y = 1/sqrt(x): y <- y + y*(0.5 - 0.5*x*y*y)
+    double hx = 0.5 * x;
+    double e = fma(-hx * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-hx * r, r, 0.5);
+    r = fma(r, e, r);
+    double s = x * r;                       // sqrt(x) ~ x * rsqrt(x)
+    double d = fma(-s, s, x);               // one correction step on the square root itself
+    return fma(d, 0.5 * r, s);
+}
+#else
+R6_HD float f32_mul(float a, float b) { return a * b; }
+R6_HD float f32_add(float a, float b) { return a + b; }
+R6_HD float f32_sub(float a, float b) { return a - b; }
+R6_HD float f32_div(float a, float b) { return a / b; }
+R6_HD float f32_sqrt(float a) { return sqrtf(a); }
+R6_HD float f32_fma(float a, float b, float c) { return fmaf(a, b, c); }
+R6_HD float f64_to_f32(double a) { return (float)a; }
+R6_HD double fast_rcp(double x) { return 1.0 / x; }
+R6_HD double fast_sqrt(double x) { return sqrt(x); }
+#endif
+
+// NumPy's float32 cos/sin for |x| < pi/4 (exact polynomial); simulator.py:204-207
+R6_HD float np_cosf_small(float x)
+{
+    float x2 = f32_mul(x, x), r;
+    r = f32_fma(0x1.98e616p-16f, x2, -0x1.6c06dcp-10f);
+    r = f32_fma(r, x2, 0x1.55553cp-05f);
+    r = f32_fma(r, x2, -0x1p-1f);
+    r = f32_fma(r, x2, 1.0f);
+    return r;
+}
+R6_HD float np_sinf_small(float x)
+{
+    float x2 = f32_mul(x, x), r;
+    r = f32_fma(0x1.7d3bbcp-19f, x2, -0x1.a06bbap-13f);
+    r = f32_fma(r, x2, 0x1.11119ap-07f);
+    r = f32_fma(r, x2, -0x1.555556p-03f);
+    r = f32_fma(r, x2, 0.0f);
+    r = f32_fma(r, x, x);
+    return r;
+}
+// OpenBLAS sdot (n = 3): float32 products, float64 sequential accumulation, one float32 rounding
+R6_HD float sdot3(float a0, float a1, float a2, float b0, float b1, float b2)
+{
+    double acc = (double)f32_mul(a0, b0);
+    acc = acc + (double)f32_mul(a1, b1);
+    acc = acc + (double)f32_mul(a2, b2);
+    return f64_to_f32(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dormand–Prince tableau (scipy rk.py:541-565) and the derived "position" tableaus.
+struct Tab {
+    double A[6][5], B[6], C[6], E[7];
+    double AA[6][5];   // AA[s][j] = sum_k A[s][k] A[k][j]   : x_s = x + h C_s v + h^2 sum_j AA[s][j] dv_j
+    double BA[6];      // BA[j]    = sum_k B[k] A[k][j]      : r_new = r + h v + h^2 sum_j BA[j] dv_j
+    double EA[6];      // EA[j]    = sum_k E[k] A[k][j] + E[6] B[j] : e_r = h^2 sum_j EA[j] dv_j
+    double P[7][4];
+};
+constexpr Tab make_tab()
+{
+    Tab t{};
+    const double A[6][5] = {
+        {0, 0, 0, 0, 0},
+        {1.0 / 5, 0, 0, 0, 0},
+        {3.0 / 40, 9.0 / 40, 0, 0, 0},
+        {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+        {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+        {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+    const double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+    const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
+    const double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+    const double P[7][4] = {
+        {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
+        {0, 0, 0, 0},
+        {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
+        {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
+        {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
+        {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
+        {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+    for (int s = 0; s < 6; s++) {
+        t.B[s] = B[s];
+        t.C[s] = C[s];
+        for (int j = 0; j < 5; j++) t.A[s][j] = A[s][j];
+    }
+    for (int j = 0; j < 7; j++) {
+        t.E[j] = E[j];
+        for (int m = 0; m < 4; m++) t.P[j][m] = P[j][m];
+    }
+    for (int s = 0; s < 6; s++)
+        for (int j = 0; j < 5; j++) {
+            double a = 0;
+            for (int k = j + 1; k < s; k++) a += A[s][k] * A[k][j];
+            t.AA[s][j] = a;
+        }
+    for (int j = 0; j < 6; j++) {
+        double b = 0, e = 0;
+        for (int k = j + 1; k < 6; k++) {
+            b += B[k] * A[k][j];
+            e += E[k] * A[k][j];
+        }
+        t.BA[j] = b;
+        t.EA[j] = e + E[6] * B[j];
+    }
+    return t;
+}
+constexpr Tab kTabHost = make_tab();
+#if defined(__CUDACC__)
+__constant__ Tab kTabDev = make_tab();   // for the rare, dynamically indexed event path
+#endif
+#if defined(__CUDA_ARCH__)
+#define R6_TAB_DYN ::r6::kTabDev
+#else
+#define R6_TAB_DYN ::r6::kTabHost
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Per-step constants consumed by the RHS
+struct StepConst {
+    double Tb0, Tb1, Tb2;   // thrust in the body frame (simulator.py:167-175)
+    double Ji1;             // 1/J_yy (= 1/J_zz), float32-valued (simulator.py:45-50)
+    double gy;              // w0 * (J0 - J1) * Ji1 : gyroscopic coupling (w0 is constant: dw0 = 0)
+    double dm;              // mass rate (simulator.py:140-141)
+    // air-density expansion around the step's initial height (simulator.py:145-150)
+    double h0, rho0, kd;    // rho(h) = rho0 * (1 - d)^p, d = kd*(h - h0), p = -(1 + g0 M / R / L)
+};
+
+// physical constants (simulator.py:39-67)
+constexpr double kG0 = 9.81;
+constexpr double kRb = 3.66 / 2;
+constexpr double kRb2 = kRb * kRb;
+constexpr double kLen2 = 40.0 * 40.0 + 3 * kRb2;
+constexpr double kSref = 3.14159265358979323846 * kRb2;
+constexpr double kRhoExp = 1 + 9.81 * 0.0289644 / 8.3144598 / (-0.0065);   // ~ -4.2559
+constexpr double kLapseOverT = 0.0065 / 288.15;
+constexpr double kCa = 0.82;
+
+R6_HD double density_exact(double h)
+{
+    // 1.225 * (T_b/(T_b + h L_b))^e  ==  1.225 * exp(-e * log(1 - c h)),  c = 0.0065/288.15
+    return 1.225 * exp(-kRhoExp * log(1.0 - kLapseOverT * h));
+}
+
+R6_HD void density_setup(StepConst &c, double h0)
+{
+    c.h0 = h0;
+    double base = 1.0 - kLapseOverT * h0;
+    c.rho0 = 1.225 * exp(-kRhoExp * log(base));
+    c.kd = kLapseOverT / base;
+}
+
+R6_HD double density(const StepConst &c, double h)
+{
+    double d = c.kd * (h - c.h0);
+    if (fabs(d) > 2e-3) return density_exact(h);   // never taken for dt = 0.1 (|dh| < 80 m)
+    // binomial series of (1 - d)^p, p = -kRhoExp, to d^6 (next term < 1e-18 for |d| <= 2e-3)
+    constexpr double p = -kRhoExp;
+    constexpr double b1 = -p;
+    constexpr double b2 = p * (p - 1) / 2;
+    constexpr double b3 = -p * (p - 1) * (p - 2) / 6;
+    constexpr double b4 = p * (p - 1) * (p - 2) * (p - 3) / 24;
+    constexpr double b5 = -p * (p - 1) * (p - 2) * (p - 3) * (p - 4) / 120;
+    constexpr double b6 = p * (p - 1) * (p - 2) * (p - 3) * (p - 4) * (p - 5) / 720;
+    double s = fma(b6, d, b5);
+    s = fma(s, d, b4);
+    s = fma(s, d, b3);
+    s = fma(s, d, b2);
+    s = fma(s, d, b1);
+    s = fma(s, d, 1.0);
+    return c.rho0 * s;
+}
+
+// env mode constants from the float32 control / initial mass
+R6_HD void consts_env_mode(StepConst &c, float m0, float u0, float u1, float u2, double w0)
+{
+    float J0 = f32_mul(f32_mul(0.5f, m0), (float)kRb2);
+    float J1 = f32_mul(f32_mul((float)(1.0 / 12), m0), (float)kLen2);
+    float Ji1 = f32_div(1.0f, J1);
+    c.Ji1 = (double)Ji1;
+    c.gy = w0 * ((double)J0 - (double)J1) * c.Ji1;
+    float cy = np_cosf_small(u0), cz = np_cosf_small(u1);
+    float sy = np_sinf_small(u0), sz = np_sinf_small(u1);
+    double T = (double)u2;
+    c.Tb0 = (double)f32_mul(cy, cz) * T;
+    c.Tb1 = (double)f32_mul(sy, cz) * T;
+    c.Tb2 = (double)sz * T;
+    c.dm = (double)f32_div(-u2, (float)(9.81 * 360));
+}
+// raw Simulator6DOF mode: python-list inputs => everything float64 (test_6DOF_simulator.py)
+R6_HD void consts_raw_mode(StepConst &c, double m0, double u0, double u1, double u2, double w0)
+{
+    double J0 = .5 * m0 * kRb2, J1 = 1.0 / 12 * m0 * kLen2;
+    c.Ji1 = 1.0 / J1;
+    c.gy = w0 * (J0 - J1) * c.Ji1;
+    double cy = cos(u0), cz = cos(u1), sy = sin(u0), sz = sin(u1);
+    c.Tb0 = (cy * cz) * u2;
+    c.Tb1 = (sy * cz) * u2;
+    c.Tb2 = sz * u2;
+    c.dm = -u2 / (9.81 * 360);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One stage derivative: dv[3], dq[4], dw1, dw2  (dr = v, dw0 = 0, dm = const are implicit)
+struct Deriv {
+    double dv0, dv1, dv2, dq0, dq1, dq2, dq3, dw1, dw2;
+};
+
+// un-normalised rotation matrix entries of the leading-scalar quaternion (q0,q1,q2,q3); R = M / n2
+struct RotU {
+    double m00, m01, m02, m10, m11, m12, m20, m21, m22, n2;
+};
+R6_HD RotU rot_unnormalised(double q0, double q1, double q2, double q3)
+{
+    RotU r;
+    double x2 = q1 * q1, y2 = q2 * q2, z2 = q3 * q3, w2 = q0 * q0;
+    double xy = q1 * q2, zw = q3 * q0, xz = q1 * q3, yw = q2 * q0, yz = q2 * q3, xw = q1 * q0;
+    r.m00 = x2 - y2 - z2 + w2; r.m01 = 2 * (xy - zw);       r.m02 = 2 * (xz + yw);
+    r.m10 = 2 * (xy + zw);     r.m11 = -x2 + y2 - z2 + w2;  r.m12 = 2 * (yz - xw);
+    r.m20 = 2 * (xz - yw);     r.m21 = 2 * (yz + xw);       r.m22 = -x2 - y2 + z2 + w2;
+    r.n2 = x2 + y2 + z2 + w2;
+    return r;
+}
+
+// simulator.py:106-143 — inputs: height, velocity, quaternion, (w1,w2), mass of the stage state
+R6_HD Deriv rhs(const StepConst &c, double w0, double h, double v0, double v1, double v2, double q0,
+                double q1, double q2, double q3, double w1, double w2, double m)
+{
+    Deriv d;
+    double rho = density(c, h);
+    RotU R = rot_unnormalised(q0, q1, q2, q3);
+    double inv = fast_rcp(R.n2 * m);       // 1 / (|q|^2 m)
+    double inv_n2 = inv * m;
+    // body-frame velocity (R^T v) and aerodynamic force (simulator.py:216-219)
+    double vb0 = R.m00 * v0 + R.m10 * v1 + R.m20 * v2;
+    double vb1 = R.m01 * v0 + R.m11 * v1 + R.m21 * v2;
+    double vb2 = R.m02 * v0 + R.m12 * v1 + R.m22 * v2;
+    double vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    double ca = (((-0.5 * rho) * vn) * kSref) * kCa * inv_n2;
+    double A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
+    double F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
+    // simulator.py:127-130, 156-165
+    d.dv0 = (R.m00 * F0 + R.m01 * F1 + R.m02 * F2) * inv - kG0;
+    d.dv1 = (R.m10 * F0 + R.m11 * F1 + R.m12 * F2) * inv;
+    d.dv2 = (R.m20 * F0 + R.m21 * F1 + R.m22 * F2) * inv;
+    // simulator.py:136, 221-229 (un-normalised quaternion)
+    d.dq0 = 0.5 * (-w0 * q1 - w1 * q2 - w2 * q3);
+    d.dq1 = 0.5 * (w0 * q0 + w2 * q2 - w1 * q3);
+    d.dq2 = 0.5 * (w1 * q0 - w2 * q1 + w0 * q3);
+    d.dq3 = 0.5 * (w2 * q0 + w1 * q1 - w0 * q2);
+    // simulator.py:137, 232-244: tau = [0, 15 T2 - 5 A2, -15 T1 + 5 A1];  J = diag(J0, J1, J1)
+    d.dw1 = c.Ji1 * (15 * c.Tb2 - 5 * A2) - c.gy * w2;
+    d.dw2 = c.Ji1 * (-15 * c.Tb1 + 5 * A1) + c.gy * w1;
+    return d;
+}
+
+// state vector layout: 0-2 r, 3-5 v, 6-9 q (scalar first), 10-12 w, 13 m
+R6_HD Deriv rhs_state(const StepConst &c, const double *y)
+{
+    return rhs(c, y[10], y[0], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]);
+}
+
+R6_HD double sq(double x) { return x * x; }
+
+// ------------------------------------------------------------------------------------------------
+// Terminal height event: rebuild the stages of the accepted step, form the quartic dense output
+// (rk.py:178-180, 715-737) and locate y[0] = 0 with Brent's method as scipy.optimize.brentq does
+// (ivp.py:52-77, xtol = rtol = 4 eps, maxiter 100).  Rare (once per episode) => not inlined.
+struct Dense {
+    double t_old, h;
+    double y_old[14];
+    double Q[14][4];
+};
+R6_HD double dense_x(const Dense &d, double t)
+{
+    double x = (t - d.t_old) / d.h;
+    double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
+    double s = d.Q[0][0] * p0 + d.Q[0][1] * p1 + d.Q[0][2] * p2 + d.Q[0][3] * p3;
+    return d.h * s + d.y_old[0];
+}
+R6_HD bool sgn(double x) { return signbit(x); }
+
+R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, out: y(t_event) */,
+                                  const Deriv &f0, double t_old, double t_new)
+{
+    const Tab &T = R6_TAB_DYN;
+    Dense d;
+    d.t_old = t_old;
+    d.h = t_new - t_old;
+    const double h = d.h;
+    double K[7][14];
+    for (int i = 0; i < 14; i++) d.y_old[i] = y[i];
+    // K[0]
+    {
+        double *k = K[0];
+        k[0] = y[3]; k[1] = y[4]; k[2] = y[5];
+        k[3] = f0.dv0; k[4] = f0.dv1; k[5] = f0.dv2;
+        k[6] = f0.dq0; k[7] = f0.dq1; k[8] = f0.dq2; k[9] = f0.dq3;
+        k[10] = 0; k[11] = f0.dw1; k[12] = f0.dw2; k[13] = c.dm;
+    }
+    double ys[14];
+    for (int s = 1; s <= 6; s++) {
+        for (int i = 0; i < 14; i++) {
+            double a = 0;
+            if (s < 6) { for (int j = 0; j < s; j++) a += K[j][i] * T.A[s][j]; }
+            else       { for (int j = 0; j < 6; j++) a += K[j][i] * T.B[j]; }
+            ys[i] = y[i] + h * a;
+        }
+        Deriv f = rhs_state(c, ys);
+        double *k = K[s];
+        k[0] = ys[3]; k[1] = ys[4]; k[2] = ys[5];
+        k[3] = f.dv0; k[4] = f.dv1; k[5] = f.dv2;
+        k[6] = f.dq0; k[7] = f.dq1; k[8] = f.dq2; k[9] = f.dq3;
+        k[10] = 0; k[11] = f.dw1; k[12] = f.dw2; k[13] = c.dm;
+    }
+    for (int i = 0; i < 14; i++)
+        for (int m = 0; m < 4; m++) {
+            double a = 0;
+            for (int j = 0; j < 7; j++) a += K[j][i] * T.P[j][m];
+            d.Q[i][m] = a;
+        }
+    // brentq
+    const double eps4 = 4 * 2.220446049250313e-16;
+    double xpre = t_old, xcur = t_new, xblk = 0, fblk = 0, spre = 0, scur = 0;
+    double fpre = dense_x(d, xpre), fcur = dense_x(d, xcur);
+    double root = xcur;
+    if (fpre == 0) root = xpre;
+    else if (fcur == 0) root = xcur;
+    else if (sgn(fpre) == sgn(fcur)) root = xcur;   // scipy raises; cannot happen after the sign test
+    else {
+        for (int it = 0; it < 100; it++) {
+            if (fpre != 0 && fcur != 0 && (sgn(fpre) != sgn(fcur))) {
+                xblk = xpre; fblk = fpre; spre = scur = xcur - xpre;
+            }
+            if (fabs(fblk) < fabs(fcur)) {
+                xpre = xcur; xcur = xblk; xblk = xpre;
+                fpre = fcur; fcur = fblk; fblk = fpre;
+            }
+            double delta = (eps4 + eps4 * fabs(xcur)) / 2;
+            double sbis = (xblk - xcur) / 2;
+            if (fcur == 0 || fabs(sbis) < delta) break;
+            if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+                double stry;
+                if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
+                else {
+                    double dpre = (fpre - fcur) / (xpre - xcur);
+                    double dblk = (fblk - fcur) / (xblk - xcur);
+                    stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+                }
+                double lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
+                if (2 * fabs(stry) < lim) { spre = scur; scur = stry; }
+                else { spre = sbis; scur = sbis; }
+            } else { spre = sbis; scur = sbis; }
+            xpre = xcur; fpre = fcur;
+            if (fabs(scur) > delta) xcur += scur;
+            else xcur += (sbis > 0 ? delta : -delta);
+            fcur = dense_x(d, xcur);
+        }
+        root = xcur;
+    }
+    // y = sol(root)
+    double x = (root - d.t_old) / d.h;
+    double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
+    for (int i = 0; i < 14; i++) {
+        double s = d.Q[i][0] * p0 + d.Q[i][1] * p1 + d.Q[i][2] * p2 + d.Q[i][3] * p3;
+        y[i] = d.h * s + d.y_old[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve_ivp(fun, [t, t+dt], y, events=height) with all defaults.  y in/out (quaternion NOT yet
+// re-normalised).  Returns the scipy status (0 / 1 / -1); natt = accepted + rejected RK attempts.
+R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt)
+{
+    constexpr Tab T = make_tab();   // compile-time: every coefficient folds into an immediate
+    constexpr double rtol = 1e-3, atol = 1e-6;
+    constexpr double inv_sqrt14 = 0.2672612419124244;   // 1/sqrt(14)
+    const double t_bound = t + dt;
+    const double w0 = y[10];
+    density_setup(c, y[0]);
+    Deriv f = rhs_state(c, y);                                   // rk.py:96
+    // ---- select_initial_step (common.py:68-134), order 4 ----
+    double h_abs;
+    {
+        const double L = fabs(t_bound - t);
+        double isc[14];
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int i = 0; i < 14; i++) {
+            isc[i] = fast_rcp(atol + fabs(y[i]) * rtol);
+            s0 += sq(y[i] * isc[i]);
+        }
+        const double fv[14] = {y[3], y[4], y[5], f.dv0, f.dv1, f.dv2, f.dq0, f.dq1, f.dq2, f.dq3, 0.0, f.dw1, f.dw2, c.dm};
+#pragma unroll
+        for (int i = 0; i < 14; i++) s1 += sq(fv[i] * isc[i]);
+        double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, L);
+        // f1 = RHS(y + h0 f0)
+        Deriv f1 = rhs(c, w0, y[0] + h0 * y[3], y[3] + h0 * f.dv0, y[4] + h0 * f.dv1, y[5] + h0 * f.dv2,
+                       y[6] + h0 * f.dq0, y[7] + h0 * f.dq1, y[8] + h0 * f.dq2, y[9] + h0 * f.dq3,
+                       y[11] + h0 * f.dw1, y[12] + h0 * f.dw2, y[13] + h0 * c.dm);
+        // (f1 - f0)/scale : position rows are h0*dv, w0 and mass rows are 0
+        double s2 = sq(h0 * f.dv0 * isc[0]) + sq(h0 * f.dv1 * isc[1]) + sq(h0 * f.dv2 * isc[2]);
+        s2 += sq((f1.dv0 - f.dv0) * isc[3]) + sq((f1.dv1 - f.dv1) * isc[4]) + sq((f1.dv2 - f.dv2) * isc[5]);
+        s2 += sq((f1.dq0 - f.dq0) * isc[6]) + sq((f1.dq1 - f.dq1) * isc[7]) + sq((f1.dq2 - f.dq2) * isc[8]) +
+              sq((f1.dq3 - f.dq3) * isc[9]);
+        s2 += sq((f1.dw1 - f.dw1) * isc[11]) + sq((f1.dw2 - f.dw2) * isc[12]);
+        double d2 = fast_sqrt(s2) * inv_sqrt14 / h0;
+        double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
+                                                  : exp(0.2 * log(0.01 / fmax(d1, d2)));
+        h_abs = fmin(fmin(100 * h0, h1), L);
+    }
+    double g = y[0];
+    int status = -2;
+    natt = 0;
+    while (status == -2) {
+        // ---- RungeKutta._step_impl (rk.py:111-176) ----
+        const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false, failed = false;
+        double t_new = t, h = 0;
+        double yn[14];
+        Deriv fn;
+        for (;;) {
+            if (h_abs < min_step) { failed = true; break; }
+            t_new = t + h_abs;
+            if (t_new - t_bound > 0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+            natt++;
+            const double h2 = h * h;
+            // ---- rk_step (rk.py:14-71) with the position rows eliminated ----
+            Deriv K[6];
+            K[0] = f;
+#pragma unroll
+            for (int s = 1; s < 6; s++) {
+                double av0 = 0, av1 = 0, av2 = 0, aq0 = 0, aq1 = 0, aq2 = 0, aq3 = 0, aw1 = 0, aw2 = 0, ax = 0;
+#pragma unroll
+                for (int j = 0; j < s; j++) {
+                    const double a = T.A[s][j];
+                    if (a != 0) {
+                        av0 = fma(a, K[j].dv0, av0); av1 = fma(a, K[j].dv1, av1); av2 = fma(a, K[j].dv2, av2);
+                        aq0 = fma(a, K[j].dq0, aq0); aq1 = fma(a, K[j].dq1, aq1);
+                        aq2 = fma(a, K[j].dq2, aq2); aq3 = fma(a, K[j].dq3, aq3);
+                        aw1 = fma(a, K[j].dw1, aw1); aw2 = fma(a, K[j].dw2, aw2);
+                    }
+                    const double aa = T.AA[s][j];
+                    if (aa != 0) ax = fma(aa, K[j].dv0, ax);
+                }
+                const double hc = h * T.C[s];
+                K[s] = rhs(c, w0, fma(h2, ax, fma(hc, y[3], y[0])),
+                           fma(h, av0, y[3]), fma(h, av1, y[4]), fma(h, av2, y[5]),
+                           fma(h, aq0, y[6]), fma(h, aq1, y[7]), fma(h, aq2, y[8]), fma(h, aq3, y[9]),
+                           fma(h, aw1, y[11]), fma(h, aw2, y[12]), fma(hc, c.dm, y[13]));
+            }
+            // y_new and the stage part of the error estimate (rk.py:66, 104-105)
+            double bv0 = 0, bv1 = 0, bv2 = 0, bq0 = 0, bq1 = 0, bq2 = 0, bq3 = 0, bw1 = 0, bw2 = 0;
+            double br0 = 0, br1 = 0, br2 = 0;
+            double ev0 = 0, ev1 = 0, ev2 = 0, eq0 = 0, eq1 = 0, eq2 = 0, eq3 = 0, ew1 = 0, ew2 = 0;
+            double er0 = 0, er1 = 0, er2 = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const double b = T.B[j], e = T.E[j], ba = T.BA[j], ea = T.EA[j];
+                if (b != 0) {
+                    bv0 = fma(b, K[j].dv0, bv0); bv1 = fma(b, K[j].dv1, bv1); bv2 = fma(b, K[j].dv2, bv2);
+                    bq0 = fma(b, K[j].dq0, bq0); bq1 = fma(b, K[j].dq1, bq1);
+                    bq2 = fma(b, K[j].dq2, bq2); bq3 = fma(b, K[j].dq3, bq3);
+                    bw1 = fma(b, K[j].dw1, bw1); bw2 = fma(b, K[j].dw2, bw2);
+                }
+                if (e != 0) {
+                    ev0 = fma(e, K[j].dv0, ev0); ev1 = fma(e, K[j].dv1, ev1); ev2 = fma(e, K[j].dv2, ev2);
+                    eq0 = fma(e, K[j].dq0, eq0); eq1 = fma(e, K[j].dq1, eq1);
+                    eq2 = fma(e, K[j].dq2, eq2); eq3 = fma(e, K[j].dq3, eq3);
+                    ew1 = fma(e, K[j].dw1, ew1); ew2 = fma(e, K[j].dw2, ew2);
+                }
+                if (ba != 0) { br0 = fma(ba, K[j].dv0, br0); br1 = fma(ba, K[j].dv1, br1); br2 = fma(ba, K[j].dv2, br2); }
+                if (ea != 0) { er0 = fma(ea, K[j].dv0, er0); er1 = fma(ea, K[j].dv1, er1); er2 = fma(ea, K[j].dv2, er2); }
+            }
+            yn[0] = fma(h2, br0, fma(h, y[3], y[0]));
+            yn[1] = fma(h2, br1, fma(h, y[4], y[1]));
+            yn[2] = fma(h2, br2, fma(h, y[5], y[2]));
+            yn[3] = fma(h, bv0, y[3]); yn[4] = fma(h, bv1, y[4]); yn[5] = fma(h, bv2, y[5]);
+            yn[6] = fma(h, bq0, y[6]); yn[7] = fma(h, bq1, y[7]); yn[8] = fma(h, bq2, y[8]); yn[9] = fma(h, bq3, y[9]);
+            yn[10] = w0;
+            yn[11] = fma(h, bw1, y[11]); yn[12] = fma(h, bw2, y[12]);
+            yn[13] = fma(h, c.dm, y[13]);
+            fn = rhs_state(c, yn);                                // K[6] = f_new (rk.py:67-69)
+            {
+                const double e6 = T.E[6];
+                ev0 = fma(e6, fn.dv0, ev0); ev1 = fma(e6, fn.dv1, ev1); ev2 = fma(e6, fn.dv2, ev2);
+                eq0 = fma(e6, fn.dq0, eq0); eq1 = fma(e6, fn.dq1, eq1); eq2 = fma(e6, fn.dq2, eq2); eq3 = fma(e6, fn.dq3, eq3);
+                ew1 = fma(e6, fn.dw1, ew1); ew2 = fma(e6, fn.dw2, ew2);
+            }
+            // error norm (rk.py:107-109, 141-142); rows w0 and mass contribute exactly 0
+            const double ee[14] = {h2 * er0, h2 * er1, h2 * er2, h * ev0, h * ev1, h * ev2, h * eq0, h * eq1,
+                                   h * eq2, h * eq3, 0.0, h * ew1, h * ew2, 0.0};
+            double ssum = 0;
+#pragma unroll
+            for (int i = 0; i < 14; i++) {
+                if (i == 10 || i == 13) continue;
+                const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), rtol, atol);
+                ssum += sq(ee[i] * fast_rcp(sc));
+            }
+            const double err = fast_sqrt(ssum) * inv_sqrt14;
+            if (err < 1) {
+                double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * exp(-0.2 * log(err)));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= fmax(0.2, 0.9 * exp(-0.2 * log(err)));
+            rejected = true;
+        }
+        if (failed) { status = -1; break; }
+        // accepted: ivp.py:659-699
+        const double t_old = t;
+        const double g_new = yn[0];
+        const bool ev = (g <= 0 && g_new >= 0) || (g >= 0 && g_new <= 0);
+        t = t_new;
+        if (t - t_bound >= 0) status = 0;
+        if (ev) {
+            event_resolve(c, y, f, t_old, t_new);
+            status = 1;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 14; i++) y[i] = yn[i];
+            f = fn;
+        }
+        g = g_new;
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// t_go of rocket_env.py:528-546: largest positive real root of f(t) = c0 t^4 + c2 t^2 + c3 t + c4
+// (np.roots' first eigenvalue with imag == 0 and real > 0 is the largest positive real root,
+// SURVEY §A.4).  Bracketing strategy (f''' > 0 on t > 0 so f' is convex there):
+//   * t_i = sqrt(-c2/(6 c0)) is the inflection point; f is convex on (t_i, inf).
+//   * if f(t_i) <= 0 the largest root lies in the convex region: Newton from an upper bound is monotone.
+//   * else if f' >= 0 at t_i, f is increasing on t > 0: single root in (0, t_i), f concave there:
+//     Newton from the left is monotone.
+//   * else f has a local minimum at s2 > t_i (found by monotone Newton on the convex f'); the largest
+//     root is right of s2 if f(s2) <= 0, otherwise it is the single root left of t_i.
+// Every Newton step is safeguarded by the bracket (falls back to bisection), so it terminates.
+R6_HD double quartic_f(double c0, double c2, double c3, double c4, double t)
+{
+    double t2 = t * t;
+    return fma(fma(c0, t2, c2), t2, fma(c3, t, c4));
+}
+R6_HD double quartic_df(double c0, double c2, double c3, double t)
+{
+    return fma(fma(4 * c0, t * t, 2 * c2), t, c3);
+}
+R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
+{
+    if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return NAN;       // no sign change => no positive root
+    // Fujiwara bound on the root moduli
+    const double a2 = fabs(c2) / c0, a1 = fabs(c3) / c0, a0 = fabs(c4) / c0;
+    double B = 2 * fmax(sqrt(a2), fmax(cbrt(a1), sqrt(sqrt(0.5 * a0))));
+    if (!(B > 0) || !isfinite(B)) return NAN;
+    double lo = 0, hi = B;
+    bool from_right = true;
+    const double ti = (c2 < 0) ? sqrt(-c2 / (6 * c0)) : 0.0;
+    if (ti > 0 && ti < B) {
+        const double fi = quartic_f(c0, c2, c3, c4, ti);
+        if (fi <= 0) { lo = ti; }
+        else {
+            const double gi = quartic_df(c0, c2, c3, ti);
+            if (gi >= 0) { hi = ti; from_right = false; }
+            else {
+                // local minimum s2 > ti: monotone Newton on f' (convex on t > 0) from the right
+                double s = B;
+                for (int it = 0; it < 60; it++) {
+                    double d1 = quartic_df(c0, c2, c3, s);
+                    double d2 = fma(12 * c0, s * s, 2 * c2);
+                    if (!(d2 > 0)) break;
+                    double sn = s - d1 / d2;
+                    if (!(sn < s) || sn <= ti) { break; }
+                    s = sn;
+                }
+                const double fs = quartic_f(c0, c2, c3, c4, s);
+                if (fs <= 0) { lo = s; }
+                else {
+                    // f(s) may be marginally positive only through rounding when s is not converged;
+                    // confirm with the true minimum bracket: f > 0 on [ti, inf) => root left of ti
+                    hi = ti; from_right = false;
+                }
+            }
+        }
+    }
+    double flo = quartic_f(c0, c2, c3, c4, lo), fhi = quartic_f(c0, c2, c3, c4, hi);
+    if (flo == 0 && lo > 0) return lo;
+    if (!(flo < 0) || !(fhi > 0)) {
+        if (fhi == 0) return hi;
+        return NAN;
+    }
+    double x = from_right ? hi : lo;
+    double fx = from_right ? fhi : flo;
+    for (int it = 0; it < 100; it++) {
+        double dfx = quartic_df(c0, c2, c3, x);
+        double xn = x - fx / dfx;
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);          // safeguard
+        double fn_ = quartic_f(c0, c2, c3, c4, xn);
+        if (fn_ > 0) hi = xn; else if (fn_ < 0) lo = xn; else return xn;
+        const double dx = fabs(xn - x);
+        x = xn; fx = fn_;
+        if (dx <= 2.220446049250313e-16 * fabs(x)) break;
+        if (hi - lo <= 2.220446049250313e-16 * hi) break;
+    }
+    // final polish (two unconditional Newton steps; converged iterates do not move)
+    for (int it = 0; it < 2; it++) {
+        double dfx = quartic_df(c0, c2, c3, x);
+        if (dfx != 0) {
+            double xn = x - quartic_f(c0, c2, c3, c4, x) / dfx;
+            if (xn > 0 && fabs(xn - x) <= 1e-9 * x) x = xn;
+        }
+    }
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-derived thresholds for the Euler-angle limit tests (computed once per call on the host)
+struct AngleTests {
+    // violation test |e_i| > L_i (rocket_env.py:366-369): mode 0 = never (L >= range), 1 = compare
+    int viol_mode[3];
+    double viol_thr[3];    // cos(L0), sin(L1), cos(L2)
+    // landing test |e_i| < L_i (rocket_env.py:386-388): mode 0 = never (L <= 0), 1 = compare, 2 = always
+    int land_mode[3];
+    double land_thr[3];
+};
+inline AngleTests make_angle_tests(const double viol[3], const double land[3])
+{
+    AngleTests a;
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < 3; i++) {
+        const double range = (i == 1) ? pi / 2 : pi;     // |e1| <= pi/2, |e0|,|e2| <= pi
+        a.viol_mode[i] = (viol[i] >= range) ? 0 : 1;
+        a.viol_thr[i] = (i == 1) ? sin(viol[i]) : cos(viol[i]);
+        if (viol[i] < 0) { a.viol_mode[i] = 2; }          // |e| > negative: always
+        a.land_mode[i] = (land[i] > range) ? 2 : ((land[i] <= 0) ? 0 : 1);
+        a.land_thr[i] = (i == 1) ? sin(land[i]) : cos(land[i]);
+    }
+    return a;
+}
+
+// Extrinsic zyx Euler angles of the float32-cast quaternion (scipy _rotation_xp.py:365-401,
+// 1052-1111), reduced to what the env needs: the two limit tests.  With a = w-y, b = z-x, c = y+w,
+// d = -x-z:  cos(e0) = (ac+bd)/(|ab||cd|), sin(e1) = (|cd|^2-|ab|^2)/(|ab|^2+|cd|^2),
+// cos(e2) = (ac-bd)/(|ab||cd|); gimbal lock (|e1 +- pi/2| <= 1e-7): e0 = 2 hs or -2 hd, e2 = 0.
+R6_HD void euler_limit_tests(const AngleTests &at, double w, double x, double y, double z, bool &violated,
+                             bool &land_ok)
+{
+    const double a = w - y, b = z - x, c = y + w, d = -x - z;
+    const double Q2 = a * a + b * b, P2 = c * c + d * d;
+    constexpr double tan2_lock = 2.5e-15;     // tan(5e-8)^2
+    const bool case1 = P2 <= tan2_lock * Q2;
+    const bool case2 = Q2 <= tan2_lock * P2;
+    double cos0, cos2;
+    if (!(case1 || case2)) {
+        const double inv = fast_rcp(fast_sqrt(Q2 * P2));
+        cos0 = (a * c + b * d) * inv;
+        cos2 = (a * c - b * d) * inv;
+    } else if (case1) {
+        cos0 = (a * a - b * b) / Q2; cos2 = 1.0;
+    } else {
+        cos0 = (c * c - d * d) / P2; cos2 = 1.0;
+    }
+    const double sin1 = (P2 - Q2) / (P2 + Q2);
+    const double m[3] = {cos0, fabs(sin1), cos2};
+    violated = false;
+    land_ok = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        // |e| > L  <=>  cos e < cos L  (i = 0, 2)   |  |sin e1| > sin L (i = 1)
+        bool v = (i == 1) ? (m[i] > at.viol_thr[i]) : (m[i] < at.viol_thr[i]);
+        v = (at.viol_mode[i] == 1) ? v : (at.viol_mode[i] == 2);
+        bool l = (i == 1) ? (m[i] < at.land_thr[i]) : (m[i] > at.land_thr[i]);
+        l = (at.land_mode[i] == 1) ? l : (at.land_mode[i] == 2);
+        violated = violated || v;
+        land_ok = land_ok || l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rocket_env.py:509-521 for a float32 action array
+R6_HD void denormalize_action(const R6Params &p, float a0, float a1, float a2, float &u0, float &u1, float &u2)
+{
+    u0 = f64_to_f32((double)a0 * p.max_gimbal);
+    u1 = f64_to_f32((double)a1 * p.max_gimbal);
+    u2 = f32_mul(f32_div(f32_add(a2, 1.0f), 2.0f), p.max_thrust);
+}
+
+struct PostOut {
+    double reward;        // after the out-of-bounds penalty, before ClipReward
+    double terms[R6_NTERMS];
+    uint32_t flags;       // R6_F_* (EVENT, OOB and the five landing flags)
+    bool tgo_missing;
+};
+
+// rocket_env.py:206-231 after the simulator step.  S = post-step state with the quaternion already
+// re-normalised in float64 (simulator.py:97).
+R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConst &c, const double *S, float u2,
+                     float v0_episode, int status, PostOut &o)
+{
+    float s[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) s[i] = f64_to_f32(S[i]);                      // :206
+    const float m = s[13];
+    const bool oob = !(s[0] >= p.bounds_low[0] && s[0] <= p.bounds_high[0] && s[1] >= p.bounds_low[1] &&
+                       s[1] <= p.bounds_high[1] && s[2] >= p.bounds_low[2] && s[2] <= p.bounds_high[2]);   // :591-593
+    const float vn = f32_sqrt(sdot3(s[3], s[4], s[5], s[3], s[4], s[5]));
+    const float rn = f32_sqrt(sdot3(s[0], s[1], s[2], s[0], s[1], s[2]));
+    bool att_viol, att_land;
+    euler_limit_tests(at, (double)s[6], (double)s[7], (double)s[8], (double)s[9], att_viol, att_land);
+    double shaping;
+    o.tgo_missing = false;
+    if (!p.shaping_velocity) {
+        // _compute_atarg (:526-566)
+        const double c0 = (-9.81) * (-9.81);
+        const float c2 = f32_mul(-4.0f, f32_mul(vn, vn));
+        const float c3 = f32_mul(-24.0f, sdot3(s[0], s[1], s[2], s[3], s[4], s[5]));
+        const float c4 = f32_mul(-36.0f, f32_mul(rn, rn));
+        const double tgo = tgo_largest_root(c0, (double)c2, (double)c3, (double)c4);
+        o.tgo_missing = !(tgo > 0);
+        const double itg = 1.0 / tgo, itg2 = 1.0 / (tgo * tgo);
+        const double q0 = (double)f32_mul(-6.0f, s[0]) * itg2 - (double)f32_mul(4.0f, s[3]) * itg + 9.81;
+        const double q1 = (double)f32_mul(-6.0f, s[1]) * itg2 - (double)f32_mul(4.0f, s[4]) * itg;
+        const double q2 = (double)f32_mul(-6.0f, s[2]) * itg2 - (double)f32_mul(4.0f, s[5]) * itg;
+        const double U = (double)f32_div(p.max_thrust, m);
+        const double qn = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double k = (qn <= U) ? 1.0 : U / qn;
+        // thrust acceleration from the float64 post-step quaternion (:339-340, simulator.py:177-186)
+        RotU R = rot_unnormalised(S[6], S[7], S[8], S[9]);
+        const double im = 1.0 / (R.n2 * (double)m);
+        const double d0 = (R.m00 * c.Tb0 + R.m01 * c.Tb1 + R.m02 * c.Tb2) * im - q0 * k;
+        const double d1 = (R.m10 * c.Tb0 + R.m11 * c.Tb1 + R.m12 * c.Tb2) * im - q1 * k;
+        const double d2 = (R.m20 * c.Tb0 + R.m21 * c.Tb1 + R.m22 * c.Tb2) * im - q2 * k;
+        shaping = p.alfa * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    } else {
+        // _compute_vtarg (:646-674) + :349
+        double rh0, rh1, rh2, vh0, tau;
+        if ((double)s[0] > p.waypoint) {
+            rh0 = (double)s[0] - p.waypoint; rh1 = s[1]; rh2 = s[2];
+            vh0 = (double)s[3] + 2.0; tau = 20;
+        } else {
+            rh0 = (double)f32_add(s[0], 1.0f); rh1 = 0; rh2 = 0;
+            vh0 = (double)s[3] + 1.0; tau = 100;
+        }
+        const double rh = sqrt(rh0 * rh0 + rh1 * rh1 + rh2 * rh2);
+        const double vh = sqrt(vh0 * vh0 + (double)s[4] * (double)s[4] + (double)s[5] * (double)s[5]);
+        const double tg = rh / vh, kk = 1 - exp(-tg / tau), den = fmax(1e-3, rh);
+        const double mv0 = (double)(-v0_episode);
+        const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * kk;
+        const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * kk;
+        const double d2 = (double)s[5] - (mv0 * (rh2 / den)) * kk;
+        shaping = p.alfa * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    }
+    const float pen = f32_mul(p.beta, u2);                                     // :355
+    const double att = att_viol ? p.gamma : 0.0;                               // :366-369
+    // landing conditions (:382-390)
+    const bool f_zero = s[0] <= p.zero_height_tol;
+    const bool f_vel = vn < p.maximum_v;
+    const bool f_rad = rn < p.target_r;
+    const bool f_att = att_land;
+    const bool f_om = fabs((double)s[10]) < p.omega_lim[0] || fabs((double)s[11]) < p.omega_lim[1] ||
+                      fabs((double)s[12]) < p.omega_lim[2];
+    const double goal = (f_zero && f_vel && f_rad && f_att && f_om) ? p.kappa : 0.0;
+    const float dr = f32_sub(p.max_r_f, rn);
+    const double final_pos = dr > 0 ? (double)f32_mul(dr, p.w_r_f) : 0.0;      // :400
+    const float dv = f32_sub(p.max_v_f, vn);
+    const double final_vel = (rn < p.max_r_f && f_zero) ? (dv > 0 ? (double)f32_mul(dv, p.w_v_f) : 0.0) : 0.0;   // :401
+    double reward = 0;
+    reward += shaping; reward += (double)pen; reward += p.eta; reward += att; reward += goal;
+    reward += final_pos; reward += final_vel;                                  // :362
+    if (oob) reward += p.oob_penalty;                                          // :228-229
+    o.reward = reward;
+    o.terms[0] = shaping; o.terms[1] = (double)pen; o.terms[2] = p.eta; o.terms[3] = att;
+    o.terms[4] = goal; o.terms[5] = final_pos; o.terms[6] = final_vel;
+    uint32_t fl = 0;
+    if (status != 0) fl |= R6_F_EVENT;
+    if (oob) fl |= R6_F_OOB;
+    if (f_zero) fl |= R6_F_ZERO_HEIGHT;
+    if (f_vel) fl |= R6_F_VEL_LIMIT;
+    if (f_rad) fl |= R6_F_LAND_RADIUS;
+    if (f_att) fl |= R6_F_ATT_LIMIT;
+    if (f_om) fl |= R6_F_OMEGA_LIMIT;
+    o.flags = fl;
+}
+
+R6_HD void normalize_quat(double *y)    // simulator.py:97, 153-154
+{
+    const double n = sqrt(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]);
+    y[6] /= n; y[7] /= n; y[8] /= n; y[9] /= n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: key = seed, counter = (env lo, env hi, a, b)
+struct U4 { uint32_t x, y, z, w; };
+R6_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+R6_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        U4 n;
+        n.x = hi1 ^ ctr.y ^ k0; n.y = lo1; n.z = hi0 ^ ctr.w ^ k1; n.w = lo0;
+        ctr = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// 53-bit uniform in [0,1) from two 32-bit words (the construction of numpy's random_sample)
+R6_HD double u53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+constexpr uint32_t kStreamReset = 0x52534554u;    // 'RSET' + block index
+constexpr uint32_t kStreamAction = 0x41435431u;   // 'ACT1'
+
+// Rocket6DOF.reset (rocket_env.py:180-199): Box.sample (float64 uniform, cast to float32), float32
+// quaternion normalisation, float32 initial condition.
+R6_HD void sample_initial_condition(const R6Params &p, uint64_t seed, uint64_t genv, uint32_t episode, float *ic)
+{
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int b = 0; b < 7; b++) {
+        U4 ctr = {(uint32_t)genv, (uint32_t)(genv >> 32), episode, kStreamReset + (uint32_t)b};
+        U4 r = philox4x32_10(ctr, k0, k1);
+        const double ua = u53(r.x, r.y), ub = u53(r.z, r.w);
+        const int i = 2 * b;
+        ic[i] = f64_to_f32((double)p.ic_low[i] + ((double)p.ic_high[i] - (double)p.ic_low[i]) * ua);
+        ic[i + 1] = f64_to_f32((double)p.ic_low[i + 1] + ((double)p.ic_high[i + 1] - (double)p.ic_low[i + 1]) * ub);
+    }
+}
+R6_HD void normalize_ic_quaternion(float *ic)      // rocket_env.py:190 (float32, sdot rule)
+{
+    double acc = (double)f32_mul(ic[6], ic[6]);
+    acc = acc + (double)f32_mul(ic[7], ic[7]);
+    acc = acc + (double)f32_mul(ic[8], ic[8]);
+    acc = acc + (double)f32_mul(ic[9], ic[9]);
+    const float n = f32_sqrt(f64_to_f32(acc));
+#pragma unroll
+    for (int i = 6; i < 10; i++) ic[i] = f32_div(ic[i], n);
+}
+// synthetic random policy: uniform(-1,1) float32, one Philox block per (env, step)
+R6_HD void philox_action(uint64_t seed, uint64_t genv, uint64_t step, float &a0, float &a1, float &a2)
+{
+    U4 ctr = {(uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)step, kStreamAction ^ (uint32_t)(step >> 32)};
+    U4 r = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double s = 1.0 / 4294967296.0;
+    a0 = f64_to_f32(-1.0 + 2.0 * (((double)r.x + 0.5) * s));
+    a1 = f64_to_f32(-1.0 + 2.0 * (((double)r.y + 0.5) * s));
+    a2 = f64_to_f32(-1.0 + 2.0 * (((double)r.z + 0.5) * s));
+    // the float32 cast may round to +-1 exactly; that is inside the action space
+}
+
+// ------------------------------------------------------------------------------------------------
+// Registers carried by the thread that owns an environment, and the glue of one env step
+struct Env {
+    double y[14];
+    float m0, v0;
+    int k;             // steps taken in the episode
+    uint32_t episode;  // episodes started so far (RNG counter)
+    double ep_return;
+};
+
+// Rocket6DOF.reset: new initial condition (Philox or replay table), Simulator6DOF re-created.
+R6_HD void env_reset(const R6Params &p, const R6Buffers &b, uint64_t seed, int64_t genv, Env &e)
+{
+    float ic[14];
+    if (b.ic_table != nullptr && b.ic_table_len > 0) {
+        const int64_t row = (genv + b.n_global * (int64_t)e.episode) % b.ic_table_len;
+#pragma unroll
+        for (int c = 0; c < 14; c++) ic[c] = b.ic_table[row * 14 + c];   // rows are already normalised
+    } else {
+        sample_initial_condition(p, seed, (uint64_t)genv, e.episode, ic);
+        normalize_ic_quaternion(ic);
+    }
+#pragma unroll
+    for (int c = 0; c < 14; c++) e.y[c] = (double)ic[c];
+    e.m0 = ic[13];
+    e.v0 = f32_sqrt(sdot3(ic[3], ic[4], ic[5], ic[3], ic[4], ic[5]));
+    e.k = 0;
+    e.episode += 1;
+    e.ep_return = 0.0;
+}
+
+struct StepOut {
+    double reward;     // what the (wrapped) env returns
+    uint32_t flags;
+    bool finished;     // done or truncated
+    int natt;
+    int status;
+    PostOut post;
+};
+
+// One Rocket6DOF.step on the registers of `e` (no reset here).
+R6_HD void env_step(const R6Params &p, const AngleTests &at, const double *__restrict__ t_table,
+                                         Env &e, float a0, float a1, float a2, StepOut &o)
+{
+    float u0, u1, u2;
+    denormalize_action(p, a0, a1, a2, u0, u1, u2);
+    StepConst c;
+    consts_env_mode(c, e.m0, u0, u1, u2, e.y[10]);
+    const int kk = e.k < p.n_t ? e.k : p.n_t - 1;
+    const double t = t_table[kk];
+    o.status = integrate(c, e.y, t, p.dt, o.natt);
+    normalize_quat(e.y);
+    e.k += 1;
+    post_step(p, at, c, e.y, u2, e.v0, o.status, o.post);
+    uint32_t fl = o.post.flags;
+    const bool done = (fl & (R6_F_EVENT | R6_F_OOB)) != 0;                    // rocket_env.py:213
+    const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit
+    if (trunc) fl |= R6_F_TRUNCATED;
+    double r = o.post.reward;
+    if (p.clip_reward) r = fmin(fmax(r, p.clip_lo), p.clip_hi);               // main_6DOF.py:40-42
+    o.reward = r;
+    o.flags = fl;
+    o.finished = done || trunc;
+    e.ep_return += r;
+}
+
+
+}  // namespace r6

@@ -1,0 +1,369 @@
+// r6_kernels.cu — sm_100a kernels + the C ABI of include/r6dof.h.
+//
+// One thread owns one environment: its 14 float64 state components are loaded from the
+// component-major (SoA) state array with fully coalesced 8-byte accesses (a warp reads 256
+// contiguous bytes per component), stay in registers through the whole adaptive RK45 step, the
+// reward / termination logic and the auto-reset, and are written back the same way.  There is no
+// tensor-core work here (the dynamics are not a contraction); the bound is the FP64 pipe.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <string.h>
+
+#include "r6_core.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+        return R6_ECUDA;
+    }
+    return R6_OK;
+}
+
+constexpr int kThreads = 128;
+
+using namespace r6;
+
+// ---------------------------------------------------------------------------------------------
+// Per-block episode statistics: warp shuffle reduction, one atomic per slot per block.
+struct StatAcc {
+    double v[R6_NSTATS];
+};
+__device__ __forceinline__ void stats_flush(const StatAcc &s, double *stats)
+{
+    __shared__ double sm[kThreads / 32][R6_NSTATS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < R6_NSTATS; k++) {
+        double x = s.v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < R6_NSTATS) {
+        double x = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) x += sm[w][threadIdx.x];
+        if (x != 0) atomicAdd(&stats[threadIdx.x], x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Env registers carried by a thread
+__device__ __forceinline__ void env_load(const R6Buffers &b, int64_t n, int64_t i, Env &e)
+{
+#pragma unroll
+    for (int c = 0; c < 14; c++) e.y[c] = b.state[(int64_t)c * n + i];
+    e.m0 = b.m0[i];
+    e.v0 = b.v0[i];
+    e.k = b.step_count[i];
+    e.episode = b.episode_id[i];
+    e.ep_return = b.ep_return[i];
+}
+__device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t i, const Env &e)
+{
+#pragma unroll
+    for (int c = 0; c < 14; c++) b.state[(int64_t)c * n + i] = e.y[c];
+    b.m0[i] = e.m0;
+    b.v0[i] = e.v0;
+    b.step_count[i] = e.k;
+    b.episode_id[i] = e.episode;
+    b.ep_return[i] = e.ep_return;
+}
+
+__device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, const R6Params &p, const double *y)
+{
+#pragma unroll
+    for (int c = 0; c < 14; c++) obs[(int64_t)c * n + i] = f64_to_f32(y[c] / p.normalizer[c]);   // rocket_env.py:503-504
+}
+
+__device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const Env &e)
+{
+    s.v[R6_S_STEPS] += 1.0;
+    if (o.finished) {
+        s.v[R6_S_EPISODES] += 1.0;
+        s.v[R6_S_RETURN_SUM] += e.ep_return;
+        s.v[R6_S_LENGTH_SUM] += (double)e.k;
+        if ((o.flags & R6_F_LANDING_ALL) == R6_F_LANDING_ALL) s.v[R6_S_LANDED] += 1.0;
+        if (o.flags & R6_F_EVENT) s.v[R6_S_GROUND] += 1.0;
+        if (o.flags & R6_F_OOB) s.v[R6_S_OOB] += 1.0;
+        if (o.flags & R6_F_TRUNCATED) s.v[R6_S_TRUNCATED] += 1.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+reset_kernel(const R6Params p, const R6Buffers b, int64_t n, int64_t env_offset, const uint8_t *mask, uint64_t seed)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    Env e;
+    e.episode = b.episode_id[i];
+    env_reset(p, b, seed, env_offset + i, e);
+    env_store(b, n, i, e);
+    write_obs(b.obs, n, i, p, e.y);
+}
+
+__global__ void __launch_bounds__(kThreads)
+step_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n, int64_t env_offset,
+            const float *__restrict__ actions, uint64_t seed)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    StatAcc st;
+#pragma unroll
+    for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
+    if (i < n) {
+        Env e;
+        env_load(b, n, i, e);
+        const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+        StepOut o;
+        env_step(p, at, b.t_table, e, a0, a1, a2, o);
+        b.reward[i] = o.reward;
+        b.done[i] = o.finished ? 1 : 0;
+        b.flags[i] = (uint8_t)o.flags;
+        if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
+        if (b.status) b.status[i] = (int8_t)o.status;
+        if (b.reward_terms) {
+#pragma unroll
+            for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
+        }
+        stats_add(st, o, e);
+        if (o.finished && p.auto_reset) {
+            // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
+            write_obs(b.terminal_obs, n, i, p, e.y);
+#pragma unroll
+            for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+            if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+            env_reset(p, b, seed, env_offset + i, e);
+        }
+        write_obs(b.obs, n, i, p, e.y);
+        env_store(b, n, i, e);
+    }
+    if (b.stats) stats_flush(st, b.stats);
+}
+
+// k fused steps, state in registers; actions from Philox / buffer (MLP variant below).
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n, int64_t env_offset, int k_steps,
+               const float *__restrict__ act_buf, uint64_t seed, int64_t step_base, float *traj_obs, float *traj_act,
+               float *traj_rew, uint8_t *traj_done)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    StatAcc st;
+#pragma unroll
+    for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
+    if (i < n) {
+        Env e;
+        env_load(b, n, i, e);
+        StepOut o;
+        o.reward = 0; o.flags = 0; o.finished = false; o.natt = 0; o.status = 0;
+        for (int j = 0; j < k_steps; j++) {
+            float a0, a1, a2;
+            if (kMode == R6_ACT_PHILOX) philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)(step_base + j), a0, a1, a2);
+            else {
+                const float *a = act_buf + ((int64_t)j * n + i) * 3;
+                a0 = a[0]; a1 = a[1]; a2 = a[2];
+            }
+            if (traj_obs) {
+#pragma unroll
+                for (int c = 0; c < 13; c++)
+                    traj_obs[((int64_t)j * 13 + c) * n + i] = f64_to_f32(e.y[c] / p.normalizer[c]);
+            }
+            if (traj_act) { float *a = traj_act + ((int64_t)j * n + i) * 3; a[0] = a0; a[1] = a1; a[2] = a2; }
+            env_step(p, at, b.t_table, e, a0, a1, a2, o);
+            if (traj_rew) traj_rew[(int64_t)j * n + i] = (float)o.reward;
+            if (traj_done) traj_done[(int64_t)j * n + i] = o.finished ? 1 : 0;
+            stats_add(st, o, e);
+            if (o.finished) {
+                if (j == k_steps - 1) {
+                    write_obs(b.terminal_obs, n, i, p, e.y);
+#pragma unroll
+                    for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+                }
+                if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+                env_reset(p, b, seed, env_offset + i, e);
+            }
+        }
+        b.reward[i] = o.reward;
+        b.done[i] = o.finished ? 1 : 0;
+        b.flags[i] = (uint8_t)o.flags;
+        if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
+        if (b.status) b.status[i] = (int8_t)o.status;
+        write_obs(b.obs, n, i, p, e.y);
+        env_store(b, n, i, e);
+    }
+    if (b.stats) stats_flush(st, b.stats);
+}
+
+// Simulator6DOF.step, raw (all-float64) mode
+__global__ void __launch_bounds__(kThreads)
+sim_raw_kernel(double *state, const double *u, const double *m0, const double *t, double dt, int64_t n,
+               int8_t *status, uint8_t *nattempts)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double y[14];
+#pragma unroll
+    for (int c = 0; c < 14; c++) y[c] = state[(int64_t)c * n + i];
+    StepConst c;
+    consts_raw_mode(c, m0[i], u[i], u[n + i], u[2 * n + i], y[10]);
+    int natt;
+    const int st = integrate(c, y, t[i], dt, natt);
+    normalize_quat(y);
+#pragma unroll
+    for (int k = 0; k < 14; k++) state[(int64_t)k * n + i] = y[k];
+    status[i] = (int8_t)st;
+    if (nattempts) nattempts[i] = (uint8_t)natt;
+}
+
+__global__ void __launch_bounds__(kThreads)
+tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i]);
+}
+
+// FMA-pipe micro-benchmark: 8 independent chains per thread
+template <typename T>
+__global__ void __launch_bounds__(256) peak_fma_kernel(int iters, double *sink)
+{
+    T a[8];
+    const T m = (T)1.0000001, c = (T)1e-9;
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (T)(threadIdx.x + k) * (T)1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = a[k] * m + c;
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == (T)123.456) sink[0] = (double)s;
+}
+
+int64_t blocks_for(int64_t n) { return (n + kThreads - 1) / kThreads; }
+
+int validate(const R6Params *p, const R6Buffers *b, int64_t n)
+{
+    if (!p || !b) return fail(R6_EINVAL, "null params/buffers%s");
+    if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (!b->state || !b->m0 || !b->v0 || !b->step_count || !b->episode_id || !b->ep_return || !b->obs)
+        return fail(R6_EINVAL, "a required state buffer is null%s");
+    return R6_OK;
+}
+int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
+{
+    int rc = validate(p, b, n);
+    if (rc) return rc;
+    if (!b->reward || !b->done || !b->flags || !b->terminal_obs || !b->terminal_state || !b->t_table)
+        return fail(R6_EINVAL, "a required output buffer is null%s");
+    if (p->n_t < 1) return fail(R6_EINVAL, "t_table is empty%s");
+    return R6_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int r6_abi_version(void) { return R6_ABI_VERSION; }
+const char *r6_last_error(void) { return g_err; }
+int r6_params_size(void) { return (int)sizeof(R6Params); }
+int r6_buffers_size(void) { return (int)sizeof(R6Buffers); }
+
+int r6_reset(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, const uint8_t *mask, uint64_t seed,
+             void *stream)
+{
+    int rc = validate(p, b, n);
+    if (rc) return rc;
+    if (n == 0) return R6_OK;
+    reset_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, n, env_offset, mask, seed);
+    return check_launch("r6_reset");
+}
+
+int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, const float *actions, uint64_t seed,
+            void *stream)
+{
+    int rc = validate_step(p, b, n);
+    if (rc) return rc;
+    if (!actions) return fail(R6_EINVAL, "actions is null%s");
+    if (n == 0) return R6_OK;
+    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
+    step_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, at, n, env_offset, actions, seed);
+    return check_launch("r6_step");
+}
+
+int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, int32_t k, int32_t mode,
+               const R6Mlp *mlp, const float *act_buf, uint64_t seed, int64_t step_base, float *traj_obs,
+               float *traj_act, float *traj_rew, uint8_t *traj_done, void *stream)
+{
+    int rc = validate_step(p, b, n);
+    if (rc) return rc;
+    if (k < 0) return fail(R6_EINVAL, "k < 0%s");
+    if (n == 0 || k == 0) return R6_OK;
+    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
+    const unsigned g = (unsigned)blocks_for(n);
+    cudaStream_t s = (cudaStream_t)stream;
+    (void)mlp;
+    if (mode == R6_ACT_PHILOX)
+        rollout_kernel<R6_ACT_PHILOX><<<g, kThreads, 0, s>>>(*p, *b, at, n, env_offset, k, nullptr, seed, step_base,
+                                                             traj_obs, traj_act, traj_rew, traj_done);
+    else if (mode == R6_ACT_BUFFER) {
+        if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
+        rollout_kernel<R6_ACT_BUFFER><<<g, kThreads, 0, s>>>(*p, *b, at, n, env_offset, k, act_buf, seed, step_base,
+                                                             traj_obs, traj_act, traj_rew, traj_done);
+    } else
+        return fail(R6_EINVAL, "unsupported action mode%s");
+    return check_launch("r6_rollout");
+}
+
+int r6_sim_step_raw(double *state, const double *u, const double *m0, const double *t, double dt, int64_t n,
+                    int8_t *status, uint8_t *nattempts, void *stream)
+{
+    if (!state || !u || !m0 || !t || !status) return fail(R6_EINVAL, "null pointer%s");
+    if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (n == 0) return R6_OK;
+    sim_raw_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, u, m0, t, dt, n, status, nattempts);
+    return check_launch("r6_sim_step_raw");
+}
+
+int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo, void *stream)
+{
+    if (!c2 || !c3 || !c4 || !tgo) return fail(R6_EINVAL, "null pointer%s");
+    if (n <= 0) return n == 0 ? R6_OK : fail(R6_EINVAL, "n < 0%s");
+    tgo_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(c2, c3, c4, c0, n, tgo);
+    return check_launch("r6_tgo");
+}
+
+int r6_stats_reset(double *stats, void *stream)
+{
+    if (!stats) return fail(R6_EINVAL, "null pointer%s");
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * R6_NSTATS, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(R6_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return R6_OK;
+}
+
+int r6_peak_fma(int32_t fp64, int64_t blocks, int32_t iters, double *sink, void *stream)
+{
+    if (!sink || blocks <= 0 || iters <= 0) return fail(R6_EINVAL, "bad argument%s");
+    if (fp64) peak_fma_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else peak_fma_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    return check_launch("r6_peak_fma");
+}
+
+}  // extern "C"

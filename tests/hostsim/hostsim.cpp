@@ -1,0 +1,94 @@
+// hostsim.cpp — TEST-ONLY host compilation of rl_rocket_6dof_b200/csrc/r6_core.cuh.
+//
+// Lets the CPU test-suite (-m "not gpu") run the exact per-environment code of the CUDA kernels
+// against the oracle before any GPU time is spent.  It is built by
+// tests/hostsim/__init__.py with g++ into tests/hostsim/_build/ and is never imported, linked or
+// shipped by the product package, which has no CPU path and fails without its CUDA library.
+#include <string.h>
+
+#include "../../rl_rocket_6dof_b200/csrc/r6_core.cuh"
+
+using namespace r6;
+
+extern "C" {
+
+struct HsEnv {
+    double y[14];
+    float m0, v0;
+    int32_t k;
+    uint32_t episode;
+    double ep_return;
+};
+struct HsOut {
+    double state[14];
+    float obs[14];
+    double reward;
+    double terms[7];
+    int32_t flags, finished, natt, status, tgo_missing;
+};
+
+int hs_sizeof_env(void) { return (int)sizeof(HsEnv); }
+int hs_sizeof_out(void) { return (int)sizeof(HsOut); }
+
+void hs_step(const R6Params *p, const double *t_table, HsEnv *envs, int64_t n, const float *actions, HsOut *outs)
+{
+    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
+    for (int64_t i = 0; i < n; i++) {
+        Env e;
+        memcpy(e.y, envs[i].y, sizeof e.y);
+        e.m0 = envs[i].m0; e.v0 = envs[i].v0; e.k = envs[i].k; e.episode = envs[i].episode;
+        e.ep_return = envs[i].ep_return;
+        StepOut o;
+        env_step(*p, at, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o);
+        memcpy(envs[i].y, e.y, sizeof e.y);
+        envs[i].k = e.k; envs[i].ep_return = e.ep_return;
+        HsOut &r = outs[i];
+        memcpy(r.state, e.y, sizeof e.y);
+        for (int c = 0; c < 14; c++) r.obs[c] = f64_to_f32(e.y[c] / p->normalizer[c]);
+        r.reward = o.reward;
+        memcpy(r.terms, o.post.terms, sizeof r.terms);
+        r.flags = (int32_t)o.flags; r.finished = o.finished; r.natt = o.natt; r.status = o.status;
+        r.tgo_missing = o.post.tgo_missing;
+    }
+}
+
+void hs_reset(const R6Params *p, const R6Buffers *b, HsEnv *envs, int64_t n, int64_t env_offset, uint64_t seed)
+{
+    for (int64_t i = 0; i < n; i++) {
+        Env e;
+        e.episode = envs[i].episode;
+        env_reset(*p, *b, seed, env_offset + i, e);
+        memcpy(envs[i].y, e.y, sizeof e.y);
+        envs[i].m0 = e.m0; envs[i].v0 = e.v0; envs[i].k = e.k; envs[i].episode = e.episode;
+        envs[i].ep_return = e.ep_return;
+    }
+}
+
+int hs_sim_step_raw(double *y, const double *u, double m0, double t, double dt, int *natt)
+{
+    StepConst c;
+    consts_raw_mode(c, m0, u[0], u[1], u[2], y[10]);
+    int st = integrate(c, y, t, dt, *natt);
+    normalize_quat(y);
+    return st;
+}
+
+double hs_tgo(double c0, double c2, double c3, double c4) { return tgo_largest_root(c0, c2, c3, c4); }
+
+void hs_euler_tests(const double viol[3], const double land[3], const double q[4], int *violated, int *land_ok)
+{
+    const AngleTests at = make_angle_tests(viol, land);
+    bool v, l;
+    euler_limit_tests(at, q[0], q[1], q[2], q[3], v, l);
+    *violated = v; *land_ok = l;
+}
+
+void hs_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    U4 r = philox4x32_10(U4{c0, c1, c2, c3}, k0, k1);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void hs_philox_action(uint64_t seed, uint64_t genv, uint64_t step, float a[3]) { philox_action(seed, genv, step, a[0], a[1], a[2]); }
+
+}  // extern "C"

@@ -17,8 +17,15 @@ REWARD_FLOOR = 1e-3
 REWARD_FLOOR_TRAJ = 0.1
 
 
+_CACHE = {}
+
+
 def golden(name):
-    return np.load(os.path.join(GOLDEN, name + ".npz"))
+    """Loads a fixture once, fully decompressed (NpzFile re-reads the archive on every access)."""
+    if name not in _CACHE:
+        with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+            _CACHE[name] = {k: z[k] for k in z.files}
+    return _CACHE[name]
 
 
 def env_params(**over):
