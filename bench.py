@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — 6DOF env-steps/s of the batched CUDA env step on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl b200|reference]
+
+A "step" is one Rocket6DOF env-step for every env of the batch (workload: BASELINE.json configs[2],
+2^20 envs per GPU, uniform random actions, auto-reset on).  Rank 0 prints ONE JSON line:
+  value      whole-job env-steps/s, one r6_step launch per env-step, actions already in HBM
+  e2e        the same through Rocket6DOFVecEnv.step_host: pinned-host actions in, H2D copy, kernel,
+             D2H copy of obs/reward/done/flags every step
+  roofline   the step kernel against the measured FP64 FMA-pipe peak (bound "fp64"; the dynamics are
+             not a contraction and sit above the HBM ridge) and roofline_hbm against MEASURED_PEAKS
+  cpu_baseline  the CPU oracle (C restatement, all host threads) on a bounded sample of the workload
+--impl reference times the CPU restatements of the reference (Python/SciPy port under a
+SubprocVecEnv-like harness; the C oracle's number is reported beside it).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "6dof_env_steps_per_sec"
+UNIT = "env-steps/s"
+F_FIX, F_ATT = 985.0, 1850.0          # algorithmic FP64 flops per env-step: 985 + 1850 * attempts
+BYTES_PER_STEP = 336.0                # algorithmic HBM bytes per env-step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preroll", type=int, default=256, help="untimed env-steps to reach the steady-state episode mix")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-envs", type=int, default=32768)
+    ap.add_argument("--cpu-sample-steps", type=int, default=100)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_oracle_throughput(n_envs, n_steps, threads):
+    """C oracle (oracle/r6_oracle.c) on `threads` host threads: bounded sample of the same workload
+    (random actions; finished envs are re-seeded with fresh initial conditions on the host)."""
+    import numpy as np
+    from oracle import c_oracle as co
+    from rl_rocket_6dof_b200.params import derive_params, load_config
+    sb3, cfg = load_config()
+    ep = derive_params(cfg, sb3)
+    rng = np.random.default_rng(0)
+
+    def sample(m):
+        ic = rng.uniform(ep.ic_low, ep.ic_high, (m, 14)).astype(np.float32)
+        q = ic[:, 6:10]
+        ic[:, 6:10] = q / np.sqrt((q * q).astype(np.float64).sum(1).astype(np.float32))[:, None]
+        return ic
+    ob = co.OracleBatch(ep, n_envs, nthreads=threads)
+    ic = sample(n_envs)
+    ob.set_state(ic.astype(np.float64), ic[:, 13], 0)
+    acts = rng.uniform(-1, 1, (8, n_envs, 3)).astype(np.float32)
+    ob.step(acts[0])
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        o = ob.step(acts[k % 8])
+        d = np.nonzero(o["done"])[0]
+        if len(d):
+            ic = sample(len(d))
+            ob.set_state(ic.astype(np.float64), ic[:, 13], 0, idx=d)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm on the host cores, all threads.  /root/reference is pure
+    Python and cannot travel to the GPU box, so the timed code is its restatement under oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": 0}
+    py = None
+    try:
+        from oracle import subproc_vec_env as sv
+        # each bench step = one VecEnv.step over `cores` workers x envs_per_worker python envs
+        py = sv.time_python_port(n_workers=cores, steps=max(args.steps, 1) * 4, warmup=max(args.warmup, 1) * 4)
+    except Exception as e:  # pragma: no cover
+        line["python_port_error"] = repr(e)[:200]
+    c_val = cpu_oracle_throughput(args.cpu_sample_envs, args.cpu_sample_steps, cores)
+    if py is not None:
+        value, kind_note = py["steps_per_s"], py["sample"]
+        ms = 1e3 * py["seconds"] / max(py["vec_steps"], 1)
+    else:
+        value, kind_note = c_val, f"C oracle, {args.cpu_sample_envs} envs x {args.cpu_sample_steps} steps"
+        ms = None
+    line.update(value=value, ms_per_step=ms,
+                config={"workload": "Rocket6DOF config.yaml, uniform random actions, auto-reset, make_env() wrappers; "
+                                    "CPU SubprocVecEnv-style harness, one worker per host core"},
+                cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": kind_note},
+                cpu_baseline_c_oracle={"value": c_val, "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": f"oracle/r6_oracle.c, {args.cpu_sample_envs} envs x "
+                                                 f"{args.cpu_sample_steps} steps, pthreads"},
+                e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from rl_rocket_6dof_b200 import _lib
+    from rl_rocket_6dof_b200.vec_env import Rocket6DOFVecEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    n = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+    # index-range sharding: rank r owns global envs [r*n, (r+1)*n); no data-path collective
+    vec = Rocket6DOFVecEnv(n, device=dev, seed=42, env_offset=rank * n, num_envs_global=world * n,
+                           record_attempts=True)
+    env = vec.batch
+    L = env.lib
+    env.reset()
+    env.rollout(args.preroll)                      # untimed: steady-state mix of episode phases
+    R = 8
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    acts = (torch.rand(R, n, 3, device=dev, generator=gen) * 2 - 1).contiguous()
+    acts_h = acts.cpu().pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- device-resident throughput: one r6_step launch per env-step -------------------------
+    for w in range(W):
+        env.step(acts[w % R])
+    env.reset_stats()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    att_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    e0.record(stream)
+    for k in range(K):
+        env.step(acts[k % R])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    ms_step = ms_total / K
+    value = world * n * K / (ms_total * 1e-3)
+    # realised RK attempts per env-step (sampled outside the timed region)
+    for k in range(4):
+        env.step(acts[k % R])
+        att_sum += env.nattempts.to(torch.float64).mean()
+    mean_att = float(att_sum) / 4
+    stats = env.stats.clone()
+    if world > 1:
+        dist.all_reduce(stats)                     # the only collective: 8 doubles of episode statistics
+    sd = env.stats_dict(stats)
+
+    # ---- fused rollout kernel (k steps per launch, in-kernel Philox actions) -----------------
+    env.rollout(K)
+    barrier()
+    e0.record(stream)
+    env.rollout(K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_roll = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+
+    # ---- end to end through the VecEnv fast path (host actions in, host obs/reward/done out) --
+    for w in range(W):
+        vec.step_host(acts_h[w % R])
+    barrier()
+    e0.record(stream)
+    for k in range(K):
+        vec.step_host(acts_h[k % R])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    e2e_value = world * n * K / (ms_e2e * 1e-3)
+
+    # ---- FP64 / FP32 FMA-pipe peak, measured here (MEASURED_PEAKS.json has none) -------------
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    peaks = {}
+    for fp64 in (1, 0):
+        blocks, iters = 148 * 8, 20000 if fp64 else 40000
+        _lib.check(L.r6_peak_fma(fp64, blocks, 100, sink.data_ptr(), stream.cuda_stream), L)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            e0.record(stream)
+            _lib.check(L.r6_peak_fma(fp64, blocks, iters, sink.data_ptr(), stream.cuda_stream), L)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            fl = 2.0 * blocks * 256 * iters * 8
+            best = max(best, fl / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        peaks["fp64" if fp64 else "fp32"] = best
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, hbm_src = measured_peaks()
+    flops_step = F_FIX + F_ATT * mean_att
+    per_gpu_steps_s = n / (ms_step * 1e-3)
+    ach_tf = per_gpu_steps_s * flops_step / 1e12
+    ach_gb = per_gpu_steps_s * BYTES_PER_STEP / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[2]: {n} envs/GPU (2^{int(np.log2(n))}), config.yaml, uniform random actions "
+                               f"U[-1,1] f32 resident in HBM, auto-reset on, make_env() wrappers fused",
+                   "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"index-range shards x{world}",
+                   "l2": "per-step working set 336 B x envs = %.0f MB > 126 MB L2" % (n * 336 / 1e6),
+                   "preroll_steps": args.preroll, "mean_rk_attempts": mean_att},
+        "gpu_launches": K,
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
+                     "frac": ach_tf / peaks["fp64"], "traffic": None,
+                     "note": "algorithmic flops/env-step = 985 + 1850 x RK attempts (SURVEY 8d) x envs per launch; "
+                             "peak = DFMA micro-benchmark measured in this run (r6_peak_fma)",
+                     "flops_per_env_step": flops_step, "kernel": "step_kernel", "launch_ms": ms_step},
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gb / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "bytes_per_env_step": BYTES_PER_STEP},
+        "peaks_measured": {"fp64_tflops": peaks["fp64"], "fp32_tflops": peaks["fp32"]},
+        "rollout_fused": {"value": world * n * K / (ms_roll * 1e-3), "unit": UNIT, "ms_per_step": ms_roll / K,
+                          "launches": 1, "actions": "in-kernel Philox4x32-10"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
+                "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
+                "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},
+        "episode_stats": {k: sd[k] for k in ("episodes", "mean_return", "mean_length", "landing_rate", "steps")},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        v = cpu_oracle_throughput(args.cpu_sample_envs, args.cpu_sample_steps, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle/r6_oracle.c (C restatement), {args.cpu_sample_envs} envs x "
+                                          f"{args.cpu_sample_steps} steps of the same workload, pthreads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 3
+#define R6_ABI_VERSION 4
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -111,6 +111,7 @@ typedef struct R6Buffers {
     uint8_t *nattempts;     /* [n] nullable: RK attempts of the step (nfev = 2 + 6*nattempts) */
     int8_t *status;         /* [n] nullable: solve_ivp status of the step (0, 1, -1) */
     float *ep_info;         /* [2][n] nullable: (return, length) of the episode that just finished */
+    float *reward_f32;      /* [n] nullable: reward[] rounded to float32 (what a VecEnv hands to SB3) */
     /* tables */
     const double *t_table;  /* [n_t] t_k = round(t_{k-1}+dt, 3) (simulator.py:92) */
     const float *ic_table;  /* [ic_table_len][14] nullable: initial conditions to replay instead of

@@ -1,0 +1,193 @@
+"""Rocket6DOFBatch — N independent Rocket6DOF environments resident on one B200.
+
+Mirrors the reference's gym contract (`reset()` / `step(a)` / observation / reward / done,
+/root/reference/my_environment/envs/rocket_env.py:180-231) for a whole batch: state lives in HBM
+as component-major float64 [14][N]; every call enqueues one hand-written CUDA kernel through the
+C ABI (include/r6dof.h) on the current torch stream.  torch is plumbing only (allocation, streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import R6Buffers, R6Mlp
+from .params import EnvParams, derive_params, load_config
+
+ACT_PHILOX, ACT_MLP, ACT_BUFFER = 0, 1, 2
+F_EVENT, F_OOB, F_TRUNCATED = 0x01, 0x02, 0x04
+F_LANDING_ALL = 0xF8
+FLAG_NAMES = ["zero_height", "velocity_limit", "landing_radius", "attitude_limit", "omega_limit"]
+STAT_NAMES = ["episodes", "return_sum", "length_sum", "landed", "ground", "out_of_bounds", "truncated", "steps"]
+
+
+class Rocket6DOFBatch:
+    """Batched env.  All tensors are CUDA tensors on `device`; nothing is computed on the host."""
+
+    def __init__(self, num_envs: int, env_config: Optional[dict] = None, sb3_config: Optional[dict] = None, *,
+                 device: str | torch.device = "cuda", seed: Optional[int] = None, auto_reset: bool = True,
+                 clip_reward: bool = True, time_limit: bool = True, env_offset: int = 0,
+                 num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
+                 ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        if params is None:
+            if env_config is None:
+                sb3_config, env_config = load_config()
+            params = derive_params(env_config, sb3_config)
+        self.params = params
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
+        self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)
+        self.num_envs_global = int(num_envs_global if num_envs_global is not None else env_offset + num_envs)
+        self.seed_value = int(params.seed if seed is None else seed)
+        self.auto_reset = auto_reset
+        self._p = params.to_struct(auto_reset=auto_reset, clip_reward=clip_reward, time_limit=time_limit)
+        n, dev = self.num_envs, self.device
+        f64, f32 = torch.float64, torch.float32
+        with torch.cuda.device(dev):
+            self.state = torch.zeros(14, n, dtype=f64, device=dev)
+            self.m0 = torch.zeros(n, dtype=f32, device=dev)
+            self.v0 = torch.zeros(n, dtype=f32, device=dev)
+            self.step_count = torch.zeros(n, dtype=torch.int32, device=dev)
+            self.episode_id = torch.zeros(n, dtype=torch.int32, device=dev)     # uint32 on the device side
+            self.ep_return = torch.zeros(n, dtype=f64, device=dev)
+            self.obs = torch.zeros(14, n, dtype=f32, device=dev)
+            self.reward = torch.zeros(n, dtype=f64, device=dev)
+            self.reward_f32 = torch.zeros(n, dtype=f32, device=dev)
+            self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.terminal_obs = torch.zeros(14, n, dtype=f32, device=dev)
+            self.terminal_state = torch.zeros(14, n, dtype=f64, device=dev)
+            self.ep_info = torch.zeros(2, n, dtype=f32, device=dev)
+            self.stats = torch.zeros(8, dtype=f64, device=dev)
+            self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
+            self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
+            self.nattempts = torch.zeros(n, dtype=torch.uint8, device=dev) if (debug_buffers or record_attempts) else None
+            self.status = torch.zeros(n, dtype=torch.int8, device=dev) if debug_buffers else None
+            self.ic_table = None
+            if ic_table is not None:
+                self.ic_table = torch.from_numpy(np.ascontiguousarray(ic_table, np.float32).reshape(-1, 14)).to(dev)
+        self._b = self._make_buffers()
+        self.steps_done = 0          # global step counter (Philox action stream)
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_buffers(self) -> R6Buffers:
+        def ptr(t):
+            return 0 if t is None else t.data_ptr()
+        b = R6Buffers()
+        b.state, b.m0, b.v0 = ptr(self.state), ptr(self.m0), ptr(self.v0)
+        b.step_count, b.episode_id, b.ep_return = ptr(self.step_count), ptr(self.episode_id), ptr(self.ep_return)
+        b.obs, b.reward, b.done, b.flags = ptr(self.obs), ptr(self.reward), ptr(self.done), ptr(self.flags)
+        b.terminal_obs, b.terminal_state = ptr(self.terminal_obs), ptr(self.terminal_state)
+        b.reward_terms, b.nattempts, b.status = ptr(self.reward_terms), ptr(self.nattempts), ptr(self.status)
+        b.ep_info = ptr(self.ep_info)
+        b.reward_f32 = ptr(self.reward_f32)
+        b.t_table = ptr(self.t_table)
+        b.ic_table = ptr(self.ic_table)
+        b.ic_table_len = 0 if self.ic_table is None else self.ic_table.shape[0]
+        b.n_global = self.num_envs_global
+        b.stats = ptr(self.stats)
+        return b
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ gym-like API (batched)
+    def seed(self, seed: int):
+        self.seed_value = int(seed)
+        return [seed]
+
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Rocket6DOF.reset for every env (or those with mask != 0). Returns obs [14, N] (view)."""
+        mp = 0
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mp = mask.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.r6_reset(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset, mp,
+                                         self.seed_value, self._stream()), self.lib)
+        return self.obs
+
+    def step(self, actions: torch.Tensor):
+        """actions: float32 CUDA tensor [N, 3] in [-1, 1].  Returns (obs[14,N], reward[N], done[N], flags[N])
+        as views of the persistent output tensors (valid until the next call)."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or actions.shape != (self.num_envs, 3):
+            raise ValueError("actions must be a float32 CUDA tensor of shape [num_envs, 3]")
+        actions = actions.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.r6_step(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset,
+                                        actions.data_ptr(), self.seed_value, self._stream()), self.lib)
+        self.steps_done += 1
+        return self.obs, self.reward, self.done, self.flags
+
+    def rollout(self, k: int, mode: int = ACT_PHILOX, *, actions: Optional[torch.Tensor] = None,
+                mlp: Optional[dict] = None, record: bool = False):
+        """k fused env-steps in one launch (state stays in registers, auto-reset on)."""
+        n = self.num_envs
+        traj = None
+        po = pa = pr = pd = 0
+        if record:
+            dev = self.device
+            traj = dict(obs=torch.empty(k, 13, n, dtype=torch.float32, device=dev),
+                        act=torch.empty(k, n, 3, dtype=torch.float32, device=dev),
+                        rew=torch.empty(k, n, dtype=torch.float32, device=dev),
+                        done=torch.empty(k, n, dtype=torch.uint8, device=dev))
+            po, pa, pr, pd = (traj[x].data_ptr() for x in ("obs", "act", "rew", "done"))
+        ab = 0
+        if mode == ACT_BUFFER:
+            if actions is None or actions.shape != (k, n, 3) or actions.dtype != torch.float32:
+                raise ValueError("ACT_BUFFER needs float32 actions [k, N, 3]")
+            actions = actions.contiguous()
+            ab = actions.data_ptr()
+        m = None
+        if mode == ACT_MLP:
+            if mlp is None:
+                raise ValueError("ACT_MLP needs the policy weights")
+            m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.r6_rollout(C.byref(self._p), C.byref(self._b), n, self.env_offset, int(k), int(mode),
+                                           C.byref(m) if m is not None else None, ab, self.seed_value,
+                                           self.steps_done, po, pa, pr, pd, self._stream()), self.lib)
+        self.steps_done += int(k)
+        return traj
+
+    # ------------------------------------------------------------------ state injection / inspection
+    def set_state(self, state: torch.Tensor, idx: Optional[torch.Tensor] = None, *, step_count: int = 0):
+        """Starts new episodes from given float32 initial conditions [M,14] (already normalised
+        quaternion), as `reset()` would after sampling them (parity runs inject the oracle's ICs)."""
+        ic = torch.as_tensor(state, dtype=torch.float32, device=self.device).reshape(-1, 14)
+        if idx is None:
+            idx = torch.arange(self.num_envs, device=self.device)
+        idx = torch.as_tensor(idx, device=self.device, dtype=torch.long).reshape(-1)
+        self.state[:, idx] = ic.t().to(torch.float64)
+        self.m0[idx] = ic[:, 13]
+        # ||v|| float32 with the sdot rule: f32 products, f64 accumulation, one rounding
+        v = ic[:, 3:6]
+        acc = (v * v).to(torch.float64).sum(1)          # products are rounded to f32 before widening
+        self.v0[idx] = acc.to(torch.float32).sqrt()
+        self.step_count[idx] = step_count
+        self.ep_return[idx] = 0
+        self.obs[:, idx] = (self.state[:, idx] / torch.as_tensor(self.params.state_normalizer, device=self.device)[:, None]).to(torch.float32)
+
+    def get_state(self) -> torch.Tensor:
+        return self.state
+
+    def reset_stats(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.r6_stats_reset(self.stats.data_ptr(), self._stream()), self.lib)
+
+    def stats_dict(self, stats: Optional[torch.Tensor] = None) -> dict:
+        s = (self.stats if stats is None else stats).detach().cpu().numpy()
+        d = dict(zip(STAT_NAMES, (float(x) for x in s)))
+        ep = max(d["episodes"], 1.0)
+        d["mean_return"] = d["return_sum"] / ep
+        d["mean_length"] = d["length_sum"] / ep
+        d["landing_rate"] = d["landed"] / ep
+        return d

@@ -134,6 +134,7 @@ step_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n,
         StepOut o;
         env_step(p, at, b.t_table, e, a0, a1, a2, o);
         b.reward[i] = o.reward;
+        if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
         b.flags[i] = (uint8_t)o.flags;
         if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
@@ -201,6 +202,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t
             }
         }
         b.reward[i] = o.reward;
+        if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
         b.flags[i] = (uint8_t)o.flags;
         if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;

@@ -1,0 +1,184 @@
+"""Rocket6DOFVecEnv — stable-baselines3-compatible VecEnv over the batched CUDA env.
+
+Drop-in for what SB3 builds around the reference's `make_env()` (main_6DOF.py:44-53):
+`Monitor(TimeLimit(ClipReward(RemoveMassFromObs(Rocket6DOF))))` inside a `DummyVecEnv`, i.e.
+13-dim float32 observations, rewards clipped to [-1, 100] as float32, `dones`, auto-reset with
+`infos[i]["terminal_observation"]`, Monitor's `infos[i]["episode"] = {"r", "l", "t"}` and
+`infos[i]["TimeLimit.truncated"]`; at done the info also carries the terminal 14-state under
+`state_history[-1]`, which is what montecarlo_script.py:33-40 reads.
+
+Two call levels:
+  * `step_host(actions)` / `reset_host()`: pinned-host-buffer fast path (no Python per-env work);
+    this is what scales to 2^20 envs and what bench.py's e2e number measures;
+  * `reset()`, `step_async()`, `step_wait()`, `step()`, ...: the SB3 VecEnv protocol on top of it
+    (info dicts are materialised only for envs that finished).
+If stable-baselines3 is importable the class is registered as a virtual subclass of its VecEnv.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .batch import F_EVENT, F_OOB, F_TRUNCATED, F_LANDING_ALL, FLAG_NAMES, Rocket6DOFBatch
+from .spaces import make_box
+
+
+class MonitorTag:
+    """Stands for stable_baselines3.common.monitor.Monitor in `env_is_wrapped` queries."""
+
+
+class Rocket6DOFVecEnv:
+    metadata = {"render.modes": []}
+
+    def __init__(self, num_envs: int, env_config: Optional[dict] = None, sb3_config: Optional[dict] = None, *,
+                 device="cuda", seed: Optional[int] = None, remove_mass_from_obs: bool = True,
+                 clip_reward: bool = True, time_limit: bool = True, **batch_kw):
+        self.batch = Rocket6DOFBatch(num_envs, env_config, sb3_config, device=device, seed=seed, auto_reset=True,
+                                     clip_reward=clip_reward, time_limit=time_limit, **batch_kw)
+        self.num_envs = int(num_envs)
+        self.obs_dim = 13 if remove_mass_from_obs else 14
+        self.observation_space = make_box(-1.0, 1.0, (self.obs_dim,), np.float32)
+        self.action_space = make_box(-1.0, 1.0, (3,), np.float32)
+        self.reward_range = (self.batch.params.clip_lo, self.batch.params.clip_hi) if clip_reward else (-np.inf, np.inf)
+        n, dev = self.num_envs, self.batch.device
+        # pinned staging buffers (host side of the boundary)
+        self._act_h = torch.empty(n, 3, dtype=torch.float32).pin_memory()
+        self._act_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        self._obs_h = torch.empty(self.obs_dim, n, dtype=torch.float32).pin_memory()
+        self._rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
+        self._done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self._flags_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self._actions = None
+        self._t_start = time.time()
+        self.h2d_bytes_per_step = self._act_h.numel() * 4
+        self.d2h_bytes_per_step = self._obs_h.numel() * 4 + self._rew_h.numel() * 4 + 2 * n
+
+    # ------------------------------------------------------------------ fast path
+    def reset_host(self) -> np.ndarray:
+        b = self.batch
+        b.reset()
+        self._obs_h.copy_(b.obs[: self.obs_dim], non_blocking=True)
+        torch.cuda.current_stream(b.device).synchronize()
+        return self._obs_h.numpy().T          # [N, obs_dim] view (strided)
+
+    def step_host(self, actions) -> tuple:
+        """actions: [N,3] float32 (numpy or CPU tensor).  Host->device copy of the actions, one step
+        kernel, device->host copy of obs / reward / done / flags; returns numpy views of the pinned
+        buffers (valid until the next call): obs [N, obs_dim], rewards [N] f32, dones [N] bool."""
+        b = self.batch
+        a = torch.as_tensor(actions, dtype=torch.float32).reshape(self.num_envs, 3)
+        if a.is_pinned():                      # caller already staged the actions in pinned memory
+            self._act_d.copy_(a, non_blocking=True)
+        else:
+            self._act_h.copy_(a)
+            self._act_d.copy_(self._act_h, non_blocking=True)
+        b.step(self._act_d)
+        self._obs_h.copy_(b.obs[: self.obs_dim], non_blocking=True)
+        self._rew_h.copy_(b.reward_f32, non_blocking=True)
+        self._done_h.copy_(b.done, non_blocking=True)
+        self._flags_h.copy_(b.flags, non_blocking=True)
+        torch.cuda.current_stream(b.device).synchronize()
+        return self._obs_h.numpy().T, self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
+
+    # ------------------------------------------------------------------ SB3 VecEnv protocol
+    def reset(self) -> np.ndarray:
+        return np.ascontiguousarray(self.reset_host())
+
+    def step_async(self, actions) -> None:
+        self._actions = np.asarray(actions, dtype=np.float32)
+
+    def step_wait(self):
+        obs, rews, dones = self.step_host(self._actions)
+        obs = np.ascontiguousarray(obs)
+        infos: List[dict] = [{} for _ in range(self.num_envs)]
+        idx = np.nonzero(dones)[0]
+        if len(idx):
+            b = self.batch
+            sel = torch.as_tensor(idx, device=b.device)
+            tobs = b.terminal_obs[: self.obs_dim][:, sel].t().cpu().numpy()
+            tstate = b.terminal_state[:, sel].t().cpu().numpy()
+            epi = b.ep_info[:, sel].cpu().numpy()
+            fl = self._flags_h.numpy()[idx]
+            now = round(time.time() - self._t_start, 6)
+            for j, i in enumerate(idx):
+                f = int(fl[j])
+                infos[i] = {
+                    "terminal_observation": tobs[j],
+                    "episode": {"r": float(epi[0, j]), "l": int(epi[1, j]), "t": now},
+                    "TimeLimit.truncated": bool(f & F_TRUNCATED),
+                    "is_done": bool(f & (F_EVENT | F_OOB)),
+                    "bounds_violation": bool(f & F_OOB),
+                    "landing_conditions": {nm: bool(f & (8 << k)) for k, nm in enumerate(FLAG_NAMES)},
+                    "is_successful": (f & F_LANDING_ALL) == F_LANDING_ALL,
+                    "state_history": [tstate[j]],
+                }
+        return obs, rews.copy(), dones.copy(), infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        return None
+
+    def seed(self, seed: Optional[int] = None) -> List[Optional[int]]:
+        if seed is not None:
+            self.batch.seed(seed)
+        return [None if seed is None else seed + i for i in range(self.num_envs)]
+
+    def render(self, mode: str = "human"):
+        raise NotImplementedError("rendering is stripped from the hot path (pyvista scene of the reference)")
+
+    def get_images(self) -> Sequence[np.ndarray]:
+        return []
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        p = self.batch.params
+        table = {"state_normalizer": p.state_normalizer, "max_thrust": p.max_thrust, "max_gimbal": p.max_gimbal,
+                 "timestep": p.timestep, "reward_coefficients": p.reward_coeff, "shaping_type": p.shaping_type,
+                 "observation_space": self.observation_space, "action_space": self.action_space,
+                 "reward_range": self.reward_range, "spec": None, "render_mode": None}
+        if attr_name not in table:
+            raise AttributeError(attr_name)
+        return [table[attr_name] for _ in self._indices(indices)]
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        raise AttributeError(f"{attr_name} is fixed at construction (kernel parameters)")
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> List[Any]:
+        if method_name == "get_state":
+            st = self.batch.state.t().cpu().numpy()
+            return [st[i] for i in self._indices(indices)]
+        if method_name == "seed":
+            return self.seed(*args, **kwargs)
+        raise AttributeError(method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:
+        name = getattr(wrapper_class, "__name__", "")
+        ok = name in ("Monitor", "MonitorTag", "TimeLimit", "ClipReward", "RemoveMassFromObs")
+        return [ok for _ in self._indices(indices)]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def getattr_depth_check(self, name: str, already_found: bool):
+        return None
+
+
+try:  # register with SB3 when it exists so isinstance(env, VecEnv) holds
+    from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv  # type: ignore
+
+    _SB3VecEnv.register(Rocket6DOFVecEnv)
+except Exception:  # pragma: no cover - SB3 is not installed in this image
+    pass
