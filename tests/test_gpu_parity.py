@@ -234,10 +234,16 @@ def test_rollout_kernel_equals_stepwise_and_is_shard_invariant():
         rews.append(b.reward.clone()); dones.append(b.done.clone())
         assert torch.equal(traj["act"][j], act)
     torch.cuda.synchronize()
-    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs)
+    # two different kernels: nvcc may contract FMAs differently, so equality is to round-off, the
+    # discrete outcomes (episode boundaries, counters) are exact
+    norm = torch.as_tensor(ep.state_normalizer, device="cuda")[:, None]
+    rel = ((a.state - b.state).abs() / torch.maximum(b.state.abs(), norm * 1e-3)).max()
+    print(f"rollout vs stepwise: max rel state diff {float(rel):.2e}")
+    assert float(rel) <= 1e-11
+    assert float((a.obs - b.obs).abs().max()) <= 2e-7
     assert torch.equal(a.step_count, b.step_count) and torch.equal(a.episode_id, b.episode_id)
-    assert torch.equal(a.ep_return, b.ep_return)
-    assert torch.equal(traj["rew"], torch.stack(rews).to(torch.float32))
+    assert float((a.ep_return - b.ep_return).abs().max()) <= 1e-6
+    assert float((traj["rew"] - torch.stack(rews).to(torch.float32)).abs().max()) <= 1e-6
     assert torch.equal(traj["done"], torch.stack(dones))
     sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
     assert np.array_equal(sa[[0, 2, 3, 4, 5, 6, 7]], sb[[0, 2, 3, 4, 5, 6, 7]]) and abs(sa[1] - sb[1]) <= 1e-9 * abs(sb[1])
@@ -249,7 +255,7 @@ def test_rollout_kernel_equals_stepwise_and_is_shard_invariant():
     s0.reset(); s1.reset()
     s0.rollout(K); s1.rollout(K)
     torch.cuda.synchronize()
-    assert torch.equal(torch.cat([s0.state, s1.state], 1), a.state)
+    assert torch.equal(torch.cat([s0.state, s1.state], 1), a.state)      # same kernel => bit-identical
     assert np.allclose(s0.stats.cpu().numpy() + s1.stats.cpu().numpy(), sa, rtol=1e-12)
 
 
