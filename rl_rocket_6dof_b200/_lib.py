@@ -53,8 +53,8 @@ def load(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
-    if os.environ.get("R6_AUTOBUILD", "1") == "1":
+    path = path or os.environ.get("R6_LIB_PATH") or LIB_PATH      # R6_LIB_PATH: A/B-test another build
+    if path == LIB_PATH and os.environ.get("R6_AUTOBUILD", "1") == "1":
         from . import build as _build
         if _build.needs_build():
             _build.build()
@@ -82,8 +82,7 @@ def load(path: str | None = None):
     L.r6_tgo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]
     L.r6_stats_reset.argtypes = [C.c_void_p, C.c_void_p]
     L.r6_peak_fma.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
-    if path == LIB_PATH:
-        _lib = L
+    _lib = L
     return L
 
 

@@ -55,9 +55,9 @@ R6_HD double fast_rcp(double x)
 }
 R6_HD double fast_sqrt(double x)
 {
-    if (x == 0.0) return 0.0;
     double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    // seed on max(x, tiny): x = 0 then gives s = 0 * r = 0 without a branch
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fmax(x, 1e-300)));
     // Newton on y = 1/sqrt(x): y <- y + y*(0.5 - 0.5*x*y*y)
     double hx = 0.5 * x;
     double e = fma(-hx * r, r, 0.5);
@@ -117,6 +117,8 @@ struct Tab {
     double BA[6];      // BA[j]    = sum_k B[k] A[k][j]      : r_new = r + h v + h^2 sum_j BA[j] dv_j
     double EA[6];      // EA[j]    = sum_k E[k] A[k][j] + E[6] B[j] : e_r = h^2 sum_j EA[j] dv_j
     double P[7][4];
+    double Psum[4];    // Psum[m]  = sum_j P[j][m]
+    double PA[6][4];   // PA[j][m] = sum_k P[k][m] A[k][j] + P[6][m] B[j] : dense output of the position rows
 };
 constexpr Tab make_tab()
 {
@@ -162,6 +164,16 @@ constexpr Tab make_tab()
         }
         t.BA[j] = b;
         t.EA[j] = e + E[6] * B[j];
+    }
+    for (int m = 0; m < 4; m++) {
+        double ps = 0;
+        for (int j = 0; j < 7; j++) ps += P[j][m];
+        t.Psum[m] = ps;
+        for (int j = 0; j < 6; j++) {
+            double a = 0;
+            for (int k = j + 1; k < 6; k++) a += P[k][m] * A[k][j];
+            t.PA[j][m] = a + P[6][m] * B[j];
+        }
     }
     return t;
 }
@@ -210,11 +222,14 @@ R6_HD void density_setup(StepConst &c, double h0)
     c.kd = kLapseOverT / base;
 }
 
+// kExact = false: binomial series of (1 - d)^p around the step's initial height, d = kd (h - h0),
+// p = -kRhoExp, to d^6; the next term is 2.6e-3 d^7, i.e. < 3e-17 for |d| <= 0.01 (|h - h0| <= 400 m).
+// The launcher picks kExact = true when dt is so large that this cannot be guaranteed (dt > 0.25 s).
+template <bool kExact>
 R6_HD double density(const StepConst &c, double h)
 {
-    double d = c.kd * (h - c.h0);
-    if (fabs(d) > 2e-3) return density_exact(h);   // never taken for dt = 0.1 (|dh| < 80 m)
-    // binomial series of (1 - d)^p, p = -kRhoExp, to d^6 (next term < 1e-18 for |d| <= 2e-3)
+    if (kExact) return density_exact(h);
+    const double d = c.kd * (h - c.h0);
     constexpr double p = -kRhoExp;
     constexpr double b1 = -p;
     constexpr double b2 = p * (p - 1) / 2;
@@ -230,6 +245,7 @@ R6_HD double density(const StepConst &c, double h)
     s = fma(s, d, 1.0);
     return c.rho0 * s;
 }
+constexpr double kMaxDtSeries = 0.25;   // (1000 m/s + 60 m/s^2 dt) dt kd <= 0.01 up to here
 
 // env mode constants from the float32 control / initial mass
 R6_HD void consts_env_mode(StepConst &c, float m0, float u0, float u1, float u2, double w0)
@@ -283,22 +299,23 @@ R6_HD RotU rot_unnormalised(double q0, double q1, double q2, double q3)
 }
 
 // simulator.py:106-143 — inputs: height, velocity, quaternion, (w1,w2), mass of the stage state
+template <bool kExact>
 R6_HD Deriv rhs(const StepConst &c, double w0, double h, double v0, double v1, double v2, double q0,
                 double q1, double q2, double q3, double w1, double w2, double m)
 {
     Deriv d;
-    double rho = density(c, h);
-    RotU R = rot_unnormalised(q0, q1, q2, q3);
-    double inv = fast_rcp(R.n2 * m);       // 1 / (|q|^2 m)
-    double inv_n2 = inv * m;
+    const double rho = density<kExact>(c, h);
+    const RotU R = rot_unnormalised(q0, q1, q2, q3);
+    const double inv = fast_rcp(R.n2 * m);       // 1 / (|q|^2 m)
+    const double inv_n2 = inv * m;
     // body-frame velocity (R^T v) and aerodynamic force (simulator.py:216-219)
-    double vb0 = R.m00 * v0 + R.m10 * v1 + R.m20 * v2;
-    double vb1 = R.m01 * v0 + R.m11 * v1 + R.m21 * v2;
-    double vb2 = R.m02 * v0 + R.m12 * v1 + R.m22 * v2;
-    double vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-    double ca = (((-0.5 * rho) * vn) * kSref) * kCa * inv_n2;
-    double A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
-    double F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
+    const double vb0 = R.m00 * v0 + R.m10 * v1 + R.m20 * v2;
+    const double vb1 = R.m01 * v0 + R.m11 * v1 + R.m21 * v2;
+    const double vb2 = R.m02 * v0 + R.m12 * v1 + R.m22 * v2;
+    const double vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    const double ca = (((-0.5 * rho) * vn) * kSref) * kCa * inv_n2;
+    const double A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
+    const double F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
     // simulator.py:127-130, 156-165
     d.dv0 = (R.m00 * F0 + R.m01 * F1 + R.m02 * F2) * inv - kG0;
     d.dv1 = (R.m10 * F0 + R.m11 * F1 + R.m12 * F2) * inv;
@@ -315,74 +332,71 @@ R6_HD Deriv rhs(const StepConst &c, double w0, double h, double v0, double v1, d
 }
 
 // state vector layout: 0-2 r, 3-5 v, 6-9 q (scalar first), 10-12 w, 13 m
+template <bool kExact>
 R6_HD Deriv rhs_state(const StepConst &c, const double *y)
 {
-    return rhs(c, y[10], y[0], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]);
+    return rhs<kExact>(c, y[10], y[0], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]);
 }
 
 R6_HD double sq(double x) { return x * x; }
-
-// ------------------------------------------------------------------------------------------------
-// Terminal height event: rebuild the stages of the accepted step, form the quartic dense output
-// (rk.py:178-180, 715-737) and locate y[0] = 0 with Brent's method as scipy.optimize.brentq does
-// (ivp.py:52-77, xtol = rtol = 4 eps, maxiter 100).  Rare (once per episode) => not inlined.
-struct Dense {
-    double t_old, h;
-    double y_old[14];
-    double Q[14][4];
-};
-R6_HD double dense_x(const Dense &d, double t)
-{
-    double x = (t - d.t_old) / d.h;
-    double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
-    double s = d.Q[0][0] * p0 + d.Q[0][1] * p1 + d.Q[0][2] * p2 + d.Q[0][3] * p3;
-    return d.h * s + d.y_old[0];
-}
 R6_HD bool sgn(double x) { return signbit(x); }
 
-R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, out: y(t_event) */,
-                                  const Deriv &f0, double t_old, double t_new)
+// ------------------------------------------------------------------------------------------------
+// Stage storage.  The Runge–Kutta stage loop is ROLLED (one copy of the right-hand side in the
+// instruction stream, coefficients read from the constant bank) and the six stage derivatives
+// K_j = (dv, dq, dw1, dw2) live outside the register file: on the device in shared memory,
+// [stage][component][thread] so that a warp touches 32 consecutive doubles (conflict-free), on the
+// host (tests/hostsim) in a local array.  This keeps the kernel near 128-168 registers instead of
+// 255, i.e. 1.5-2x the resident warps, and the hot loop inside the instruction cache.
+constexpr int kNK = 9;   // stored components per stage
+struct KLocal {
+    double k[6][kNK];
+    R6_HD double get(int j, int c) const { return k[j][c]; }
+    R6_HD void set(int j, int c, double v) { k[j][c] = v; }
+};
+#if defined(__CUDACC__)
+template <int kThreadsPerBlock>
+struct KShared {
+    double *base;   // smem + threadIdx.x
+    __device__ __forceinline__ double get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
+    __device__ __forceinline__ void set(int j, int c, double v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
+};
+#endif
+template <class KS>
+R6_HD void k_store(KS &K, int j, const Deriv &d)
+{
+    K.set(j, 0, d.dv0); K.set(j, 1, d.dv1); K.set(j, 2, d.dv2);
+    K.set(j, 3, d.dq0); K.set(j, 4, d.dq1); K.set(j, 5, d.dq2); K.set(j, 6, d.dq3);
+    K.set(j, 7, d.dw1); K.set(j, 8, d.dw2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Terminal height event (ivp.py:52-77, 134-158, 678-699): quartic dense output of the accepted step
+// (rk.py:178-180, 715-737) from the stored stages, y[0] = 0 located by Brent's method exactly as
+// scipy.optimize.brentq does (xtol = rtol = 4 eps, maxiter 100), then y = sol(t_event).
+// Position rows use the PA tableau (their stage derivatives are stage velocities), the mass row is
+// dm * Psum, the w0 row is 0.  Rare (at most once per episode) => not inlined.
+template <class KS>
+R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, out: y(t_event) */, const KS &K,
+                                  const Deriv &fn, double t_old, double t_new)
 {
     const Tab &T = R6_TAB_DYN;
-    Dense d;
-    d.t_old = t_old;
-    d.h = t_new - t_old;
-    const double h = d.h;
-    double K[7][14];
-    for (int i = 0; i < 14; i++) d.y_old[i] = y[i];
-    // K[0]
-    {
-        double *k = K[0];
-        k[0] = y[3]; k[1] = y[4]; k[2] = y[5];
-        k[3] = f0.dv0; k[4] = f0.dv1; k[5] = f0.dv2;
-        k[6] = f0.dq0; k[7] = f0.dq1; k[8] = f0.dq2; k[9] = f0.dq3;
-        k[10] = 0; k[11] = f0.dw1; k[12] = f0.dw2; k[13] = c.dm;
+    const double h = t_new - t_old;
+    double qx[4];   // Q row of the height component
+    for (int m = 0; m < 4; m++) {
+        double a = 0;
+        for (int j = 0; j < 6; j++) a += T.PA[j][m] * K.get(j, 0);
+        qx[m] = y[3] * T.Psum[m] + h * a;
     }
-    double ys[14];
-    for (int s = 1; s <= 6; s++) {
-        for (int i = 0; i < 14; i++) {
-            double a = 0;
-            if (s < 6) { for (int j = 0; j < s; j++) a += K[j][i] * T.A[s][j]; }
-            else       { for (int j = 0; j < 6; j++) a += K[j][i] * T.B[j]; }
-            ys[i] = y[i] + h * a;
-        }
-        Deriv f = rhs_state(c, ys);
-        double *k = K[s];
-        k[0] = ys[3]; k[1] = ys[4]; k[2] = ys[5];
-        k[3] = f.dv0; k[4] = f.dv1; k[5] = f.dv2;
-        k[6] = f.dq0; k[7] = f.dq1; k[8] = f.dq2; k[9] = f.dq3;
-        k[10] = 0; k[11] = f.dw1; k[12] = f.dw2; k[13] = c.dm;
-    }
-    for (int i = 0; i < 14; i++)
-        for (int m = 0; m < 4; m++) {
-            double a = 0;
-            for (int j = 0; j < 7; j++) a += K[j][i] * T.P[j][m];
-            d.Q[i][m] = a;
-        }
-    // brentq
+    const double x_old = y[0];
+    auto ev = [&](double t) {
+        const double x = (t - t_old) / h;
+        const double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
+        return h * (qx[0] * p0 + qx[1] * p1 + qx[2] * p2 + qx[3] * p3) + x_old;
+    };
     const double eps4 = 4 * 2.220446049250313e-16;
     double xpre = t_old, xcur = t_new, xblk = 0, fblk = 0, spre = 0, scur = 0;
-    double fpre = dense_x(d, xpre), fcur = dense_x(d, xcur);
+    double fpre = ev(xpre), fcur = ev(xcur);
     double root = xcur;
     if (fpre == 0) root = xpre;
     else if (fcur == 0) root = xcur;
@@ -396,79 +410,104 @@ R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, ou
                 xpre = xcur; xcur = xblk; xblk = xpre;
                 fpre = fcur; fcur = fblk; fblk = fpre;
             }
-            double delta = (eps4 + eps4 * fabs(xcur)) / 2;
-            double sbis = (xblk - xcur) / 2;
+            const double delta = (eps4 + eps4 * fabs(xcur)) / 2;
+            const double sbis = (xblk - xcur) / 2;
             if (fcur == 0 || fabs(sbis) < delta) break;
             if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
                 double stry;
                 if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
                 else {
-                    double dpre = (fpre - fcur) / (xpre - xcur);
-                    double dblk = (fblk - fcur) / (xblk - xcur);
+                    const double dpre = (fpre - fcur) / (xpre - xcur);
+                    const double dblk = (fblk - fcur) / (xblk - xcur);
                     stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
                 }
-                double lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
+                const double lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
                 if (2 * fabs(stry) < lim) { spre = scur; scur = stry; }
                 else { spre = sbis; scur = sbis; }
             } else { spre = sbis; scur = sbis; }
             xpre = xcur; fpre = fcur;
             if (fabs(scur) > delta) xcur += scur;
             else xcur += (sbis > 0 ? delta : -delta);
-            fcur = dense_x(d, xcur);
+            fcur = ev(xcur);
         }
         root = xcur;
     }
     // y = sol(root)
-    double x = (root - d.t_old) / d.h;
-    double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
-    for (int i = 0; i < 14; i++) {
-        double s = d.Q[i][0] * p0 + d.Q[i][1] * p1 + d.Q[i][2] * p2 + d.Q[i][3] * p3;
-        y[i] = d.h * s + d.y_old[i];
+    const double x = (root - t_old) / h;
+    double p[4];
+    p[0] = x; p[1] = p[0] * x; p[2] = p[1] * x; p[3] = p[2] * x;
+    double pp[7];   // pp[j] = sum_m P[j][m] p_m ; ppa[j] for the position rows ; ps = sum_m Psum[m] p_m
+    double ppa[6], ps = 0;
+    for (int j = 0; j < 7; j++) {
+        double a = 0;
+        for (int m = 0; m < 4; m++) a += T.P[j][m] * p[m];
+        pp[j] = a;
     }
+    for (int j = 0; j < 6; j++) {
+        double a = 0;
+        for (int m = 0; m < 4; m++) a += T.PA[j][m] * p[m];
+        ppa[j] = a;
+    }
+    for (int m = 0; m < 4; m++) ps += T.Psum[m] * p[m];
+    const double fnv[kNK] = {fn.dv0, fn.dv1, fn.dv2, fn.dq0, fn.dq1, fn.dq2, fn.dq3, fn.dw1, fn.dw2};
+    // positions first (they need the old velocities)
+    for (int i = 0; i < 3; i++) {
+        double a = 0;
+        for (int j = 0; j < 6; j++) a += ppa[j] * K.get(j, i);
+        y[i] = y[i] + h * (y[3 + i] * ps + h * a);
+    }
+    const int comp[kNK] = {3, 4, 5, 6, 7, 8, 9, 11, 12};
+    for (int cidx = 0; cidx < kNK; cidx++) {
+        double a = pp[6] * fnv[cidx];
+        for (int j = 0; j < 6; j++) a += pp[j] * K.get(j, cidx);
+        y[comp[cidx]] = y[comp[cidx]] + h * a;
+    }
+    y[13] = y[13] + h * (c.dm * ps);
 }
 
 // ------------------------------------------------------------------------------------------------
 // solve_ivp(fun, [t, t+dt], y, events=height) with all defaults.  y in/out (quaternion NOT yet
 // re-normalised).  Returns the scipy status (0 / 1 / -1); natt = accepted + rejected RK attempts.
-R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt)
+template <bool kExact, class KS>
+R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS &K)
 {
-    constexpr Tab T = make_tab();   // compile-time: every coefficient folds into an immediate
+    const Tab &T = R6_TAB_DYN;
     constexpr double rtol = 1e-3, atol = 1e-6;
     constexpr double inv_sqrt14 = 0.2672612419124244;   // 1/sqrt(14)
     const double t_bound = t + dt;
     const double w0 = y[10];
     density_setup(c, y[0]);
-    Deriv f = rhs_state(c, y);                                   // rk.py:96
-    // ---- select_initial_step (common.py:68-134), order 4 ----
     double h_abs;
     {
+        const Deriv f = rhs_state<kExact>(c, y);                 // rk.py:96
+        k_store(K, 0, f);
+        // ---- select_initial_step (common.py:68-134), order 4 ----
         const double L = fabs(t_bound - t);
         double isc[14];
         double s0 = 0, s1 = 0;
 #pragma unroll
         for (int i = 0; i < 14; i++) {
-            isc[i] = fast_rcp(atol + fabs(y[i]) * rtol);
+            isc[i] = fast_rcp(fma(fabs(y[i]), rtol, atol));
             s0 += sq(y[i] * isc[i]);
         }
         const double fv[14] = {y[3], y[4], y[5], f.dv0, f.dv1, f.dv2, f.dq0, f.dq1, f.dq2, f.dq3, 0.0, f.dw1, f.dw2, c.dm};
 #pragma unroll
         for (int i = 0; i < 14; i++) s1 += sq(fv[i] * isc[i]);
-        double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
+        const double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, L);
         // f1 = RHS(y + h0 f0)
-        Deriv f1 = rhs(c, w0, y[0] + h0 * y[3], y[3] + h0 * f.dv0, y[4] + h0 * f.dv1, y[5] + h0 * f.dv2,
-                       y[6] + h0 * f.dq0, y[7] + h0 * f.dq1, y[8] + h0 * f.dq2, y[9] + h0 * f.dq3,
-                       y[11] + h0 * f.dw1, y[12] + h0 * f.dw2, y[13] + h0 * c.dm);
-        // (f1 - f0)/scale : position rows are h0*dv, w0 and mass rows are 0
+        const Deriv f1 = rhs<kExact>(c, w0, y[0] + h0 * y[3], y[3] + h0 * f.dv0, y[4] + h0 * f.dv1, y[5] + h0 * f.dv2,
+                                     y[6] + h0 * f.dq0, y[7] + h0 * f.dq1, y[8] + h0 * f.dq2, y[9] + h0 * f.dq3,
+                                     y[11] + h0 * f.dw1, y[12] + h0 * f.dw2, y[13] + h0 * c.dm);
+        // (f1 - f0)/scale : position rows are h0*dv, the w0 and mass rows are 0
         double s2 = sq(h0 * f.dv0 * isc[0]) + sq(h0 * f.dv1 * isc[1]) + sq(h0 * f.dv2 * isc[2]);
         s2 += sq((f1.dv0 - f.dv0) * isc[3]) + sq((f1.dv1 - f.dv1) * isc[4]) + sq((f1.dv2 - f.dv2) * isc[5]);
         s2 += sq((f1.dq0 - f.dq0) * isc[6]) + sq((f1.dq1 - f.dq1) * isc[7]) + sq((f1.dq2 - f.dq2) * isc[8]) +
               sq((f1.dq3 - f.dq3) * isc[9]);
         s2 += sq((f1.dw1 - f.dw1) * isc[11]) + sq((f1.dw2 - f.dw2) * isc[12]);
-        double d2 = fast_sqrt(s2) * inv_sqrt14 / h0;
-        double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
-                                                  : exp(0.2 * log(0.01 / fmax(d1, d2)));
+        const double d2 = fast_sqrt(s2) * inv_sqrt14 / h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : exp(0.2 * log(0.01 / fmax(d1, d2)));
         h_abs = fmin(fmin(100 * h0, h1), L);
     }
     double g = y[0];
@@ -490,77 +529,70 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt)
             h_abs = fabs(h);
             natt++;
             const double h2 = h * h;
-            // ---- rk_step (rk.py:14-71) with the position rows eliminated ----
-            Deriv K[6];
-            K[0] = f;
-#pragma unroll
+            // ---- rk_step (rk.py:14-71): stages 2..6, rolled; position rows via the AA tableau ----
+#pragma unroll 1
             for (int s = 1; s < 6; s++) {
-                double av0 = 0, av1 = 0, av2 = 0, aq0 = 0, aq1 = 0, aq2 = 0, aq3 = 0, aw1 = 0, aw2 = 0, ax = 0;
+                double acc[kNK], ax = 0;
 #pragma unroll
+                for (int i = 0; i < kNK; i++) acc[i] = 0;
+#pragma unroll 1
                 for (int j = 0; j < s; j++) {
-                    const double a = T.A[s][j];
-                    if (a != 0) {
-                        av0 = fma(a, K[j].dv0, av0); av1 = fma(a, K[j].dv1, av1); av2 = fma(a, K[j].dv2, av2);
-                        aq0 = fma(a, K[j].dq0, aq0); aq1 = fma(a, K[j].dq1, aq1);
-                        aq2 = fma(a, K[j].dq2, aq2); aq3 = fma(a, K[j].dq3, aq3);
-                        aw1 = fma(a, K[j].dw1, aw1); aw2 = fma(a, K[j].dw2, aw2);
-                    }
-                    const double aa = T.AA[s][j];
-                    if (aa != 0) ax = fma(aa, K[j].dv0, ax);
+                    const double a = T.A[s][j], aa = T.AA[s][j];
+                    const double k0 = K.get(j, 0);
+                    acc[0] = fma(a, k0, acc[0]);
+                    ax = fma(aa, k0, ax);
+#pragma unroll
+                    for (int i = 1; i < kNK; i++) acc[i] = fma(a, K.get(j, i), acc[i]);
                 }
                 const double hc = h * T.C[s];
-                K[s] = rhs(c, w0, fma(h2, ax, fma(hc, y[3], y[0])),
-                           fma(h, av0, y[3]), fma(h, av1, y[4]), fma(h, av2, y[5]),
-                           fma(h, aq0, y[6]), fma(h, aq1, y[7]), fma(h, aq2, y[8]), fma(h, aq3, y[9]),
-                           fma(h, aw1, y[11]), fma(h, aw2, y[12]), fma(hc, c.dm, y[13]));
+                const Deriv d = rhs<kExact>(c, w0, fma(h2, ax, fma(hc, y[3], y[0])),
+                                            fma(h, acc[0], y[3]), fma(h, acc[1], y[4]), fma(h, acc[2], y[5]),
+                                            fma(h, acc[3], y[6]), fma(h, acc[4], y[7]), fma(h, acc[5], y[8]),
+                                            fma(h, acc[6], y[9]), fma(h, acc[7], y[11]), fma(h, acc[8], y[12]),
+                                            fma(hc, c.dm, y[13]));
+                k_store(K, s, d);
             }
-            // y_new and the stage part of the error estimate (rk.py:66, 104-105)
-            double bv0 = 0, bv1 = 0, bv2 = 0, bq0 = 0, bq1 = 0, bq2 = 0, bq3 = 0, bw1 = 0, bw2 = 0;
-            double br0 = 0, br1 = 0, br2 = 0;
-            double ev0 = 0, ev1 = 0, ev2 = 0, eq0 = 0, eq1 = 0, eq2 = 0, eq3 = 0, ew1 = 0, ew2 = 0;
-            double er0 = 0, er1 = 0, er2 = 0;
+            // ---- y_new and the stage part of the error estimate (rk.py:66, 104-105) ----
+            double bs[kNK], es[kNK], br[3], er[3];
 #pragma unroll
+            for (int i = 0; i < kNK; i++) { bs[i] = 0; es[i] = 0; }
+#pragma unroll
+            for (int i = 0; i < 3; i++) { br[i] = 0; er[i] = 0; }
+#pragma unroll 1
             for (int j = 0; j < 6; j++) {
                 const double b = T.B[j], e = T.E[j], ba = T.BA[j], ea = T.EA[j];
-                if (b != 0) {
-                    bv0 = fma(b, K[j].dv0, bv0); bv1 = fma(b, K[j].dv1, bv1); bv2 = fma(b, K[j].dv2, bv2);
-                    bq0 = fma(b, K[j].dq0, bq0); bq1 = fma(b, K[j].dq1, bq1);
-                    bq2 = fma(b, K[j].dq2, bq2); bq3 = fma(b, K[j].dq3, bq3);
-                    bw1 = fma(b, K[j].dw1, bw1); bw2 = fma(b, K[j].dw2, bw2);
+#pragma unroll
+                for (int i = 0; i < kNK; i++) {
+                    const double k = K.get(j, i);
+                    bs[i] = fma(b, k, bs[i]);
+                    es[i] = fma(e, k, es[i]);
+                    if (i < 3) { br[i] = fma(ba, k, br[i]); er[i] = fma(ea, k, er[i]); }
                 }
-                if (e != 0) {
-                    ev0 = fma(e, K[j].dv0, ev0); ev1 = fma(e, K[j].dv1, ev1); ev2 = fma(e, K[j].dv2, ev2);
-                    eq0 = fma(e, K[j].dq0, eq0); eq1 = fma(e, K[j].dq1, eq1);
-                    eq2 = fma(e, K[j].dq2, eq2); eq3 = fma(e, K[j].dq3, eq3);
-                    ew1 = fma(e, K[j].dw1, ew1); ew2 = fma(e, K[j].dw2, ew2);
-                }
-                if (ba != 0) { br0 = fma(ba, K[j].dv0, br0); br1 = fma(ba, K[j].dv1, br1); br2 = fma(ba, K[j].dv2, br2); }
-                if (ea != 0) { er0 = fma(ea, K[j].dv0, er0); er1 = fma(ea, K[j].dv1, er1); er2 = fma(ea, K[j].dv2, er2); }
             }
-            yn[0] = fma(h2, br0, fma(h, y[3], y[0]));
-            yn[1] = fma(h2, br1, fma(h, y[4], y[1]));
-            yn[2] = fma(h2, br2, fma(h, y[5], y[2]));
-            yn[3] = fma(h, bv0, y[3]); yn[4] = fma(h, bv1, y[4]); yn[5] = fma(h, bv2, y[5]);
-            yn[6] = fma(h, bq0, y[6]); yn[7] = fma(h, bq1, y[7]); yn[8] = fma(h, bq2, y[8]); yn[9] = fma(h, bq3, y[9]);
+            yn[0] = fma(h2, br[0], fma(h, y[3], y[0]));
+            yn[1] = fma(h2, br[1], fma(h, y[4], y[1]));
+            yn[2] = fma(h2, br[2], fma(h, y[5], y[2]));
+            yn[3] = fma(h, bs[0], y[3]); yn[4] = fma(h, bs[1], y[4]); yn[5] = fma(h, bs[2], y[5]);
+            yn[6] = fma(h, bs[3], y[6]); yn[7] = fma(h, bs[4], y[7]); yn[8] = fma(h, bs[5], y[8]); yn[9] = fma(h, bs[6], y[9]);
             yn[10] = w0;
-            yn[11] = fma(h, bw1, y[11]); yn[12] = fma(h, bw2, y[12]);
+            yn[11] = fma(h, bs[7], y[11]); yn[12] = fma(h, bs[8], y[12]);
             yn[13] = fma(h, c.dm, y[13]);
-            fn = rhs_state(c, yn);                                // K[6] = f_new (rk.py:67-69)
-            {
-                const double e6 = T.E[6];
-                ev0 = fma(e6, fn.dv0, ev0); ev1 = fma(e6, fn.dv1, ev1); ev2 = fma(e6, fn.dv2, ev2);
-                eq0 = fma(e6, fn.dq0, eq0); eq1 = fma(e6, fn.dq1, eq1); eq2 = fma(e6, fn.dq2, eq2); eq3 = fma(e6, fn.dq3, eq3);
-                ew1 = fma(e6, fn.dw1, ew1); ew2 = fma(e6, fn.dw2, ew2);
-            }
-            // error norm (rk.py:107-109, 141-142); rows w0 and mass contribute exactly 0
-            const double ee[14] = {h2 * er0, h2 * er1, h2 * er2, h * ev0, h * ev1, h * ev2, h * eq0, h * eq1,
-                                   h * eq2, h * eq3, 0.0, h * ew1, h * ew2, 0.0};
+            fn = rhs_state<kExact>(c, yn);                        // K[6] = f_new (rk.py:67-69)
+            const double e6 = T.E[6];
+            const double fnv[kNK] = {fn.dv0, fn.dv1, fn.dv2, fn.dq0, fn.dq1, fn.dq2, fn.dq3, fn.dw1, fn.dw2};
+            // error norm (rk.py:107-109, 141-142); the w0 and mass rows contribute exactly 0
             double ssum = 0;
 #pragma unroll
-            for (int i = 0; i < 14; i++) {
-                if (i == 10 || i == 13) continue;
+            for (int i = 0; i < 3; i++) {
                 const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), rtol, atol);
-                ssum += sq(ee[i] * fast_rcp(sc));
+                ssum += sq(h2 * er[i] * fast_rcp(sc));
+            }
+            const int comp[kNK] = {3, 4, 5, 6, 7, 8, 9, 11, 12};
+#pragma unroll
+            for (int i = 0; i < kNK; i++) {
+                const int ci = comp[i];
+                const double sc = fma(fmax(fabs(y[ci]), fabs(yn[ci])), rtol, atol);
+                ssum += sq(h * fma(e6, fnv[i], es[i]) * fast_rcp(sc));
             }
             const double err = fast_sqrt(ssum) * inv_sqrt14;
             if (err < 1) {
@@ -580,12 +612,12 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt)
         t = t_new;
         if (t - t_bound >= 0) status = 0;
         if (ev) {
-            event_resolve(c, y, f, t_old, t_new);
+            event_resolve(c, y, K, fn, t_old, t_new);
             status = 1;
         } else {
 #pragma unroll
             for (int i = 0; i < 14; i++) y[i] = yn[i];
-            f = fn;
+            if (status == -2) k_store(K, 0, fn);                  // first-same-as-last
         }
         g = g_new;
     }
@@ -615,13 +647,14 @@ R6_HD double quartic_df(double c0, double c2, double c3, double t)
 R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
 {
     if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return NAN;       // no sign change => no positive root
-    // Fujiwara bound on the root moduli
-    const double a2 = fabs(c2) / c0, a1 = fabs(c3) / c0, a0 = fabs(c4) / c0;
-    double B = 2 * fmax(sqrt(a2), fmax(cbrt(a1), sqrt(sqrt(0.5 * a0))));
+    // Fujiwara bound on the root moduli; float32 is plenty for a bound (inflated by 1e-4)
+    const double ic0 = fast_rcp(c0);
+    const float a2 = (float)(fabs(c2) * ic0), a1 = (float)(fabs(c3) * ic0), a0 = (float)(fabs(c4) * ic0);
+    const double B = (double)(2.0002f * fmaxf(sqrtf(a2), fmaxf(cbrtf(a1), sqrtf(sqrtf(0.5f * a0)))));
     if (!(B > 0) || !isfinite(B)) return NAN;
     double lo = 0, hi = B;
     bool from_right = true;
-    const double ti = (c2 < 0) ? sqrt(-c2 / (6 * c0)) : 0.0;
+    const double ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * (1.0 / 6)) : 0.0;
     if (ti > 0 && ti < B) {
         const double fi = quartic_f(c0, c2, c3, c4, ti);
         if (fi <= 0) { lo = ti; }
@@ -632,24 +665,20 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
                 // local minimum s2 > ti: monotone Newton on f' (convex on t > 0) from the right
                 double s = B;
                 for (int it = 0; it < 60; it++) {
-                    double d1 = quartic_df(c0, c2, c3, s);
-                    double d2 = fma(12 * c0, s * s, 2 * c2);
+                    const double d1 = quartic_df(c0, c2, c3, s);
+                    const double d2 = fma(12 * c0, s * s, 2 * c2);
                     if (!(d2 > 0)) break;
-                    double sn = s - d1 / d2;
+                    const double sn = s - d1 * fast_rcp(d2);
                     if (!(sn < s) || sn <= ti) { break; }
                     s = sn;
                 }
                 const double fs = quartic_f(c0, c2, c3, c4, s);
                 if (fs <= 0) { lo = s; }
-                else {
-                    // f(s) may be marginally positive only through rounding when s is not converged;
-                    // confirm with the true minimum bracket: f > 0 on [ti, inf) => root left of ti
-                    hi = ti; from_right = false;
-                }
+                else { hi = ti; from_right = false; }   // f > 0 on [ti, inf): the root is left of ti
             }
         }
     }
-    double flo = quartic_f(c0, c2, c3, c4, lo), fhi = quartic_f(c0, c2, c3, c4, hi);
+    const double flo = quartic_f(c0, c2, c3, c4, lo), fhi = quartic_f(c0, c2, c3, c4, hi);
     if (flo == 0 && lo > 0) return lo;
     if (!(flo < 0) || !(fhi > 0)) {
         if (fhi == 0) return hi;
@@ -658,21 +687,21 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
     double x = from_right ? hi : lo;
     double fx = from_right ? fhi : flo;
     for (int it = 0; it < 100; it++) {
-        double dfx = quartic_df(c0, c2, c3, x);
-        double xn = x - fx / dfx;
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);          // safeguard
-        double fn_ = quartic_f(c0, c2, c3, c4, xn);
+        const double dfx = quartic_df(c0, c2, c3, x);
+        double xn = x - fx * fast_rcp(dfx);
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);          // safeguard: bisection
+        const double fn_ = quartic_f(c0, c2, c3, c4, xn);
         if (fn_ > 0) hi = xn; else if (fn_ < 0) lo = xn; else return xn;
         const double dx = fabs(xn - x);
         x = xn; fx = fn_;
-        if (dx <= 2.220446049250313e-16 * fabs(x)) break;
+        if (dx <= 4.440892098500626e-16 * fabs(x)) break;
         if (hi - lo <= 2.220446049250313e-16 * hi) break;
     }
-    // final polish (two unconditional Newton steps; converged iterates do not move)
-    for (int it = 0; it < 2; it++) {
-        double dfx = quartic_df(c0, c2, c3, x);
+    // final polish: one unconditional Newton step with a true division (converged iterates barely move)
+    {
+        const double dfx = quartic_df(c0, c2, c3, x);
         if (dfx != 0) {
-            double xn = x - quartic_f(c0, c2, c3, c4, x) / dfx;
+            const double xn = x - quartic_f(c0, c2, c3, c4, x) / dfx;
             if (xn > 0 && fabs(xn - x) <= 1e-9 * x) x = xn;
         }
     }
@@ -702,6 +731,31 @@ inline AngleTests make_angle_tests(const double viol[3], const double land[3])
         a.land_thr[i] = (i == 1) ? sin(land[i]) : cos(land[i]);
     }
     return a;
+}
+
+// Everything the kernels need that is derived from R6Params on the host once per call
+struct Derived {
+    AngleTests at;
+    double inv_norm[R6_NSTATE];   // RN(1 / normalizer[i]) for the exact 3-instruction division below
+};
+inline Derived make_derived(const R6Params &p)
+{
+    Derived d;
+    d.at = make_angle_tests(p.att_traj_limit, p.land_att_limit);
+    for (int i = 0; i < R6_NSTATE; i++) d.inv_norm[i] = 1.0 / p.normalizer[i];
+    return d;
+}
+// Correctly rounded a / b from r = RN(1/b) (Markstein): q = a r; q' = q + (a - b q) r.
+// Bit-identical to the IEEE division of rocket_env.py:503-504 (b is a normal number, no overflow).
+R6_HD double div_exact(double a, double b, double rinv)
+{
+    const double q = a * rinv;
+    const double rem = fma(-q, b, a);
+    return fma(rem, rinv, q);
+}
+R6_HD float obs_component(const R6Params &p, const Derived &dv, const double *y, int i)
+{
+    return f64_to_f32(div_exact(y[i], p.normalizer[i], dv.inv_norm[i]));
 }
 
 // Extrinsic zyx Euler angles of the float32-cast quaternion (scipy _rotation_xp.py:365-401,
@@ -783,20 +837,20 @@ R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConst &c
         const float c4 = f32_mul(-36.0f, f32_mul(rn, rn));
         const double tgo = tgo_largest_root(c0, (double)c2, (double)c3, (double)c4);
         o.tgo_missing = !(tgo > 0);
-        const double itg = 1.0 / tgo, itg2 = 1.0 / (tgo * tgo);
+        const double itg = fast_rcp(tgo), itg2 = itg * itg;
         const double q0 = (double)f32_mul(-6.0f, s[0]) * itg2 - (double)f32_mul(4.0f, s[3]) * itg + 9.81;
         const double q1 = (double)f32_mul(-6.0f, s[1]) * itg2 - (double)f32_mul(4.0f, s[4]) * itg;
         const double q2 = (double)f32_mul(-6.0f, s[2]) * itg2 - (double)f32_mul(4.0f, s[5]) * itg;
         const double U = (double)f32_div(p.max_thrust, m);
-        const double qn = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
-        const double k = (qn <= U) ? 1.0 : U / qn;
+        const double qn = fast_sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double k = (qn <= U) ? 1.0 : U * fast_rcp(qn);
         // thrust acceleration from the float64 post-step quaternion (:339-340, simulator.py:177-186)
         RotU R = rot_unnormalised(S[6], S[7], S[8], S[9]);
-        const double im = 1.0 / (R.n2 * (double)m);
+        const double im = fast_rcp(R.n2 * (double)m);
         const double d0 = (R.m00 * c.Tb0 + R.m01 * c.Tb1 + R.m02 * c.Tb2) * im - q0 * k;
         const double d1 = (R.m10 * c.Tb0 + R.m11 * c.Tb1 + R.m12 * c.Tb2) * im - q1 * k;
         const double d2 = (R.m20 * c.Tb0 + R.m21 * c.Tb1 + R.m22 * c.Tb2) * im - q2 * k;
-        shaping = p.alfa * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        shaping = p.alfa * fast_sqrt(d0 * d0 + d1 * d1 + d2 * d2);
     } else {
         // _compute_vtarg (:646-674) + :349
         double rh0, rh1, rh2, vh0, tau;
@@ -850,8 +904,8 @@ R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConst &c
 
 R6_HD void normalize_quat(double *y)    // simulator.py:97, 153-154
 {
-    const double n = sqrt(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]);
-    y[6] /= n; y[7] /= n; y[8] /= n; y[9] /= n;
+    const double rn = fast_rcp(fast_sqrt(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]));
+    y[6] *= rn; y[7] *= rn; y[8] *= rn; y[9] *= rn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -957,8 +1011,9 @@ struct StepOut {
 };
 
 // One Rocket6DOF.step on the registers of `e` (no reset here).
-R6_HD void env_step(const R6Params &p, const AngleTests &at, const double *__restrict__ t_table,
-                                         Env &e, float a0, float a1, float a2, StepOut &o)
+template <bool kExact, class KS>
+R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restrict__ t_table, Env &e, float a0,
+                    float a1, float a2, StepOut &o, KS &K)
 {
     float u0, u1, u2;
     denormalize_action(p, a0, a1, a2, u0, u1, u2);
@@ -966,10 +1021,10 @@ R6_HD void env_step(const R6Params &p, const AngleTests &at, const double *__res
     consts_env_mode(c, e.m0, u0, u1, u2, e.y[10]);
     const int kk = e.k < p.n_t ? e.k : p.n_t - 1;
     const double t = t_table[kk];
-    o.status = integrate(c, e.y, t, p.dt, o.natt);
+    o.status = integrate<kExact>(c, e.y, t, p.dt, o.natt, K);
     normalize_quat(e.y);
     e.k += 1;
-    post_step(p, at, c, e.y, u2, e.v0, o.status, o.post);
+    post_step(p, dv.at, c, e.y, u2, e.v0, o.status, o.post);
     uint32_t fl = o.post.flags;
     const bool done = (fl & (R6_F_EVENT | R6_F_OOB)) != 0;                    // rocket_env.py:213
     const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit
@@ -981,6 +1036,5 @@ R6_HD void env_step(const R6Params &p, const AngleTests &at, const double *__res
     o.finished = done || trunc;
     e.ep_return += r;
 }
-
 
 }  // namespace r6

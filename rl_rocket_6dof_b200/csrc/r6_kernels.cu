@@ -34,36 +34,43 @@ int check_launch(const char *what)
 }
 
 constexpr int kThreads = 128;
+#ifndef R6_MIN_BLOCKS
+#define R6_MIN_BLOCKS 3          /* resident CTAs per SM the register allocation is tuned for */
+#endif
+constexpr int kSmemBytes = 6 * r6::kNK * kThreads * (int)sizeof(double);   // stage storage, 55,296 B per CTA
 
 using namespace r6;
+using KStore = KShared<kThreads>;
+
+__device__ __forceinline__ KStore make_kstore()
+{
+    extern __shared__ double r6_smem[];
+    KStore K;
+    K.base = r6_smem + threadIdx.x;
+    return K;
+}
 
 // ---------------------------------------------------------------------------------------------
-// Per-block episode statistics: warp shuffle reduction, one atomic per slot per block.
+// Episode statistics: warp shuffle reduction, lane 0 issues one atomic per non-zero slot.
+// (No block barrier: warps of a CTA finish their adaptive steps at different times.)
 struct StatAcc {
     double v[R6_NSTATS];
 };
 __device__ __forceinline__ void stats_flush(const StatAcc &s, double *stats)
 {
-    __shared__ double sm[kThreads / 32][R6_NSTATS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) {
         double x = s.v[k];
+        if (__any_sync(0xffffffffu, x != 0.0)) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sm[warp][k] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < R6_NSTATS) {
-        double x = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) x += sm[w][threadIdx.x];
-        if (x != 0) atomicAdd(&stats[threadIdx.x], x);
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) atomicAdd(&stats[k], x);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Env registers carried by a thread
 __device__ __forceinline__ void env_load(const R6Buffers &b, int64_t n, int64_t i, Env &e)
 {
 #pragma unroll
@@ -85,10 +92,11 @@ __device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t
     b.ep_return[i] = e.ep_return;
 }
 
-__device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, const R6Params &p, const double *y)
+__device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, const R6Params &p, const Derived &dv,
+                                          const double *y)
 {
 #pragma unroll
-    for (int c = 0; c < 14; c++) obs[(int64_t)c * n + i] = f64_to_f32(y[c] / p.normalizer[c]);   // rocket_env.py:503-504
+    for (int c = 0; c < 14; c++) obs[(int64_t)c * n + i] = obs_component(p, dv, y, c);   // rocket_env.py:503-504
 }
 
 __device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const Env &e)
@@ -107,7 +115,8 @@ __device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const En
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-reset_kernel(const R6Params p, const R6Buffers b, int64_t n, int64_t env_offset, const uint8_t *mask, uint64_t seed)
+reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, const uint8_t *mask,
+             uint64_t seed)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -116,14 +125,16 @@ reset_kernel(const R6Params p, const R6Buffers b, int64_t n, int64_t env_offset,
     e.episode = b.episode_id[i];
     env_reset(p, b, seed, env_offset + i, e);
     env_store(b, n, i, e);
-    write_obs(b.obs, n, i, p, e.y);
+    write_obs(b.obs, n, i, p, dv, e.y);
 }
 
-__global__ void __launch_bounds__(kThreads)
-step_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n, int64_t env_offset,
+template <bool kExact>
+__global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
+step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
             const float *__restrict__ actions, uint64_t seed)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    KStore K = make_kstore();
     StatAcc st;
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
@@ -132,7 +143,7 @@ step_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n,
         env_load(b, n, i, e);
         const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
         StepOut o;
-        env_step(p, at, b.t_table, e, a0, a1, a2, o);
+        env_step<kExact>(p, dv, b.t_table, e, a0, a1, a2, o, K);
         b.reward[i] = o.reward;
         if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
@@ -144,28 +155,31 @@ step_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n,
             for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
         }
         stats_add(st, o, e);
-        if (o.finished && p.auto_reset) {
-            // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
-            write_obs(b.terminal_obs, n, i, p, e.y);
-#pragma unroll
-            for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+        if (o.finished) {
             if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
-            env_reset(p, b, seed, env_offset + i, e);
+            if (p.auto_reset) {
+                // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
+                write_obs(b.terminal_obs, n, i, p, dv, e.y);
+#pragma unroll
+                for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+                env_reset(p, b, seed, env_offset + i, e);
+            }
         }
-        write_obs(b.obs, n, i, p, e.y);
+        write_obs(b.obs, n, i, p, dv, e.y);
         env_store(b, n, i, e);
     }
     if (b.stats) stats_flush(st, b.stats);
 }
 
-// k fused steps, state in registers; actions from Philox / buffer (MLP variant below).
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t n, int64_t env_offset, int k_steps,
+// k fused steps, state in registers; actions from Philox or a [k][n][3] buffer.
+template <int kMode, bool kExact>
+__global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
+rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, int k_steps,
                const float *__restrict__ act_buf, uint64_t seed, int64_t step_base, float *traj_obs, float *traj_act,
                float *traj_rew, uint8_t *traj_done)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    KStore K = make_kstore();
     StatAcc st;
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
@@ -174,6 +188,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t
         env_load(b, n, i, e);
         StepOut o;
         o.reward = 0; o.flags = 0; o.finished = false; o.natt = 0; o.status = 0;
+#pragma unroll 1
         for (int j = 0; j < k_steps; j++) {
             float a0, a1, a2;
             if (kMode == R6_ACT_PHILOX) philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)(step_base + j), a0, a1, a2);
@@ -183,17 +198,16 @@ rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t
             }
             if (traj_obs) {
 #pragma unroll
-                for (int c = 0; c < 13; c++)
-                    traj_obs[((int64_t)j * 13 + c) * n + i] = f64_to_f32(e.y[c] / p.normalizer[c]);
+                for (int c = 0; c < 13; c++) traj_obs[((int64_t)j * 13 + c) * n + i] = obs_component(p, dv, e.y, c);
             }
             if (traj_act) { float *a = traj_act + ((int64_t)j * n + i) * 3; a[0] = a0; a[1] = a1; a[2] = a2; }
-            env_step(p, at, b.t_table, e, a0, a1, a2, o);
+            env_step<kExact>(p, dv, b.t_table, e, a0, a1, a2, o, K);
             if (traj_rew) traj_rew[(int64_t)j * n + i] = (float)o.reward;
             if (traj_done) traj_done[(int64_t)j * n + i] = o.finished ? 1 : 0;
             stats_add(st, o, e);
             if (o.finished) {
                 if (j == k_steps - 1) {
-                    write_obs(b.terminal_obs, n, i, p, e.y);
+                    write_obs(b.terminal_obs, n, i, p, dv, e.y);
 #pragma unroll
                     for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
                 }
@@ -207,18 +221,20 @@ rollout_kernel(const R6Params p, const R6Buffers b, const AngleTests at, int64_t
         b.flags[i] = (uint8_t)o.flags;
         if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
         if (b.status) b.status[i] = (int8_t)o.status;
-        write_obs(b.obs, n, i, p, e.y);
+        write_obs(b.obs, n, i, p, dv, e.y);
         env_store(b, n, i, e);
     }
     if (b.stats) stats_flush(st, b.stats);
 }
 
 // Simulator6DOF.step, raw (all-float64) mode
-__global__ void __launch_bounds__(kThreads)
+template <bool kExact>
+__global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
 sim_raw_kernel(double *state, const double *u, const double *m0, const double *t, double dt, int64_t n,
                int8_t *status, uint8_t *nattempts)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    KStore K = make_kstore();
     if (i >= n) return;
     double y[14];
 #pragma unroll
@@ -226,7 +242,7 @@ sim_raw_kernel(double *state, const double *u, const double *m0, const double *t
     StepConst c;
     consts_raw_mode(c, m0[i], u[i], u[n + i], u[2 * n + i], y[10]);
     int natt;
-    const int st = integrate(c, y, t[i], dt, natt);
+    const int st = integrate<kExact>(c, y, t[i], dt, natt, K);
     normalize_quat(y);
 #pragma unroll
     for (int k = 0; k < 14; k++) state[(int64_t)k * n + i] = y[k];
@@ -257,6 +273,34 @@ __global__ void __launch_bounds__(256) peak_fma_kernel(int iters, double *sink)
 #pragma unroll
     for (int k = 0; k < 8; k++) s += a[k];
     if (s == (T)123.456) sink[0] = (double)s;
+}
+
+// kernels that keep the RK stages in dynamic shared memory need the > 48 KB opt-in once per process
+template <class F>
+int enable_smem(F kernel)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(R6_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return R6_OK;
+}
+int ensure_attributes()
+{
+    static thread_local int device_done = -1;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(R6_ECUDA, "cudaGetDevice failed%s");
+    if (dev == device_done) return R6_OK;
+    int rc = 0;
+    rc |= enable_smem(step_kernel<false>);
+    rc |= enable_smem(step_kernel<true>);
+    rc |= enable_smem(rollout_kernel<R6_ACT_PHILOX, false>);
+    rc |= enable_smem(rollout_kernel<R6_ACT_PHILOX, true>);
+    rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, false>);
+    rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, true>);
+    rc |= enable_smem(sim_raw_kernel<false>);
+    rc |= enable_smem(sim_raw_kernel<true>);
+    if (rc) return R6_ECUDA;
+    device_done = dev;
+    return R6_OK;
 }
 
 int64_t blocks_for(int64_t n) { return (n + kThreads - 1) / kThreads; }
@@ -294,7 +338,8 @@ int r6_reset(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offse
     int rc = validate(p, b, n);
     if (rc) return rc;
     if (n == 0) return R6_OK;
-    reset_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, n, env_offset, mask, seed);
+    const Derived dv = make_derived(*p);
+    reset_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, dv, n, env_offset, mask, seed);
     return check_launch("r6_reset");
 }
 
@@ -305,8 +350,12 @@ int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset
     if (rc) return rc;
     if (!actions) return fail(R6_EINVAL, "actions is null%s");
     if (n == 0) return R6_OK;
-    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
-    step_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, at, n, env_offset, actions, seed);
+    if ((rc = ensure_attributes())) return rc;
+    const Derived dv = make_derived(*p);
+    const unsigned g = (unsigned)blocks_for(n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->dt <= kMaxDtSeries) step_kernel<false><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, actions, seed);
+    else step_kernel<true><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, actions, seed);
     return check_launch("r6_step");
 }
 
@@ -318,19 +367,23 @@ int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_off
     if (rc) return rc;
     if (k < 0) return fail(R6_EINVAL, "k < 0%s");
     if (n == 0 || k == 0) return R6_OK;
-    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
+    if ((rc = ensure_attributes())) return rc;
+    const Derived dv = make_derived(*p);
     const unsigned g = (unsigned)blocks_for(n);
     cudaStream_t s = (cudaStream_t)stream;
     (void)mlp;
-    if (mode == R6_ACT_PHILOX)
-        rollout_kernel<R6_ACT_PHILOX><<<g, kThreads, 0, s>>>(*p, *b, at, n, env_offset, k, nullptr, seed, step_base,
-                                                             traj_obs, traj_act, traj_rew, traj_done);
-    else if (mode == R6_ACT_BUFFER) {
+    const bool exact = !(p->dt <= kMaxDtSeries);
+#define R6_LAUNCH_ROLLOUT(MODE, EXACT, BUF)                                                                         \
+    rollout_kernel<MODE, EXACT><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, k, BUF, seed, step_base, \
+                                                                traj_obs, traj_act, traj_rew, traj_done)
+    if (mode == R6_ACT_PHILOX) {
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, true, nullptr); else R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, false, nullptr);
+    } else if (mode == R6_ACT_BUFFER) {
         if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
-        rollout_kernel<R6_ACT_BUFFER><<<g, kThreads, 0, s>>>(*p, *b, at, n, env_offset, k, act_buf, seed, step_base,
-                                                             traj_obs, traj_act, traj_rew, traj_done);
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf);
     } else
         return fail(R6_EINVAL, "unsupported action mode%s");
+#undef R6_LAUNCH_ROLLOUT
     return check_launch("r6_rollout");
 }
 
@@ -340,7 +393,11 @@ int r6_sim_step_raw(double *state, const double *u, const double *m0, const doub
     if (!state || !u || !m0 || !t || !status) return fail(R6_EINVAL, "null pointer%s");
     if (n < 0) return fail(R6_EINVAL, "n < 0%s");
     if (n == 0) return R6_OK;
-    sim_raw_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, u, m0, t, dt, n, status, nattempts);
+    int rc = ensure_attributes();
+    if (rc) return rc;
+    const unsigned g = (unsigned)blocks_for(n);
+    if (dt <= kMaxDtSeries) sim_raw_kernel<false><<<g, kThreads, kSmemBytes, (cudaStream_t)stream>>>(state, u, m0, t, dt, n, status, nattempts);
+    else sim_raw_kernel<true><<<g, kThreads, kSmemBytes, (cudaStream_t)stream>>>(state, u, m0, t, dt, n, status, nattempts);
     return check_launch("r6_sim_step_raw");
 }
 

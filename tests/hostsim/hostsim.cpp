@@ -32,19 +32,21 @@ int hs_sizeof_out(void) { return (int)sizeof(HsOut); }
 
 void hs_step(const R6Params *p, const double *t_table, HsEnv *envs, int64_t n, const float *actions, HsOut *outs)
 {
-    const AngleTests at = make_angle_tests(p->att_traj_limit, p->land_att_limit);
+    const Derived dv = make_derived(*p);
+    KLocal K;
     for (int64_t i = 0; i < n; i++) {
         Env e;
         memcpy(e.y, envs[i].y, sizeof e.y);
         e.m0 = envs[i].m0; e.v0 = envs[i].v0; e.k = envs[i].k; e.episode = envs[i].episode;
         e.ep_return = envs[i].ep_return;
         StepOut o;
-        env_step(*p, at, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o);
+        if (p->dt <= kMaxDtSeries) env_step<false>(*p, dv, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o, K);
+        else env_step<true>(*p, dv, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o, K);
         memcpy(envs[i].y, e.y, sizeof e.y);
         envs[i].k = e.k; envs[i].ep_return = e.ep_return;
         HsOut &r = outs[i];
         memcpy(r.state, e.y, sizeof e.y);
-        for (int c = 0; c < 14; c++) r.obs[c] = f64_to_f32(e.y[c] / p->normalizer[c]);
+        for (int c = 0; c < 14; c++) r.obs[c] = obs_component(*p, dv, e.y, c);
         r.reward = o.reward;
         memcpy(r.terms, o.post.terms, sizeof r.terms);
         r.flags = (int32_t)o.flags; r.finished = o.finished; r.natt = o.natt; r.status = o.status;
@@ -68,7 +70,8 @@ int hs_sim_step_raw(double *y, const double *u, double m0, double t, double dt, 
 {
     StepConst c;
     consts_raw_mode(c, m0, u[0], u[1], u[2], y[10]);
-    int st = integrate(c, y, t, dt, *natt);
+    KLocal K;
+    int st = (dt <= kMaxDtSeries) ? integrate<false>(c, y, t, dt, *natt, K) : integrate<true>(c, y, t, dt, *natt, K);
     normalize_quat(y);
     return st;
 }
