@@ -27,7 +27,7 @@
 #define R6_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define R6_HD inline
-#define R6_HD_NOINLINE
+#define R6_HD_NOINLINE inline
 #endif
 
 namespace r6 {
@@ -208,6 +208,10 @@ constexpr double kRhoExp = 1 + 9.81 * 0.0289644 / 8.3144598 / (-0.0065);   // ~ 
 constexpr double kLapseOverT = 0.0065 / 288.15;
 constexpr double kCa = 0.82;
 
+// x^e for x > 0.  Kept out of line: it is called once or twice per RK step from four places and the
+// inlined log/exp pair costs ~150 instructions per site (instruction-cache footprint of the kernel).
+R6_HD_NOINLINE double pow_pos(double x, double e) { return exp(e * log(x)); }
+
 R6_HD double density_exact(double h)
 {
     // 1.225 * (T_b/(T_b + h L_b))^e  ==  1.225 * exp(-e * log(1 - c h)),  c = 0.0065/288.15
@@ -218,7 +222,7 @@ R6_HD void density_setup(StepConst &c, double h0)
 {
     c.h0 = h0;
     double base = 1.0 - kLapseOverT * h0;
-    c.rho0 = 1.225 * exp(-kRhoExp * log(base));
+    c.rho0 = 1.225 * pow_pos(base, -kRhoExp);
     c.kd = kLapseOverT / base;
 }
 
@@ -507,7 +511,7 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS 
               sq((f1.dq3 - f.dq3) * isc[9]);
         s2 += sq((f1.dw1 - f.dw1) * isc[11]) + sq((f1.dw2 - f.dw2) * isc[12]);
         const double d2 = fast_sqrt(s2) * inv_sqrt14 / h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : exp(0.2 * log(0.01 / fmax(d1, d2)));
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow_pos(0.01 / fmax(d1, d2), 0.2);
         h_abs = fmin(fmin(100 * h0, h1), L);
     }
     double g = y[0];
@@ -595,13 +599,14 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS 
                 ssum += sq(h * fma(e6, fnv[i], es[i]) * fast_rcp(sc));
             }
             const double err = fast_sqrt(ssum) * inv_sqrt14;
+            const double raw = (err == 0) ? 10.0 : 0.9 * pow_pos(err, -0.2);   // SAFETY * err^(-1/5)
             if (err < 1) {
-                double factor = (err == 0) ? 10.0 : fmin(10.0, 0.9 * exp(-0.2 * log(err)));
+                double factor = fmin(10.0, raw);
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 break;
             }
-            h_abs *= fmax(0.2, 0.9 * exp(-0.2 * log(err)));
+            h_abs *= fmax(0.2, raw);
             rejected = true;
         }
         if (failed) { status = -1; break; }
@@ -689,12 +694,11 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
     for (int it = 0; it < 100; it++) {
         const double dfx = quartic_df(c0, c2, c3, x);
         double xn = x - fx * fast_rcp(dfx);
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);          // safeguard: bisection
+        if (fabs(xn - x) <= 4.440892098500626e-16 * fabs(x)) break;   // converged (monotone Newton stalls at the root)
+        if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);        // safeguard: bisection
         const double fn_ = quartic_f(c0, c2, c3, c4, xn);
-        if (fn_ > 0) hi = xn; else if (fn_ < 0) lo = xn; else return xn;
-        const double dx = fabs(xn - x);
         x = xn; fx = fn_;
-        if (dx <= 4.440892098500626e-16 * fabs(x)) break;
+        if (fn_ > 0) hi = xn; else if (fn_ < 0) lo = xn; else break;
         if (hi - lo <= 2.220446049250313e-16 * hi) break;
     }
     // final polish: one unconditional Newton step with a true division (converged iterates barely move)
@@ -938,7 +942,7 @@ constexpr uint32_t kStreamAction = 0x41435431u;   // 'ACT1'
 R6_HD void sample_initial_condition(const R6Params &p, uint64_t seed, uint64_t genv, uint32_t episode, float *ic)
 {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 7; b++) {
         U4 ctr = {(uint32_t)genv, (uint32_t)(genv >> 32), episode, kStreamReset + (uint32_t)b};
         U4 r = philox4x32_10(ctr, k0, k1);

@@ -33,7 +33,10 @@ int check_launch(const char *what)
     return R6_OK;
 }
 
-constexpr int kThreads = 128;
+#ifndef R6_THREADS
+#define R6_THREADS 128           /* threads (= environments) per CTA */
+#endif
+constexpr int kThreads = R6_THREADS;
 #ifndef R6_MIN_BLOCKS
 #define R6_MIN_BLOCKS 3          /* resident CTAs per SM the register allocation is tuned for */
 #endif
