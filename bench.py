@@ -47,6 +47,18 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(envs_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch, from the committed
+    `ncu --set full` capture (profiles/step_kernel_traffic.json), scaled to this run's envs per launch."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    per_env = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["envs_per_launch"]
+    return per_env * envs_per_launch, d.get("source")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,6 +304,7 @@ def run_b200(args):
     per_gpu_steps_s = n / (ms_step * 1e-3)
     ach_tf = per_gpu_steps_s * flops_step / 1e12
     ach_gb = per_gpu_steps_s * BYTES_PER_STEP / 1e9
+    traffic, traffic_src = ncu_traffic(n)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,12 +316,13 @@ def run_b200(args):
                    "preroll_steps": args.preroll, "mean_rk_attempts": mean_att},
         "gpu_launches": K,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
-                     "frac": ach_tf / peaks["fp64"], "traffic": None,
+                     "frac": ach_tf / peaks["fp64"], "traffic": traffic, "traffic_unit": "B/launch",
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_STEP * n,
                      "note": "algorithmic flops/env-step = 985 + 1850 x RK attempts (SURVEY 8d) x envs per launch; "
                              "peak = DFMA micro-benchmark measured in this run (r6_peak_fma)",
                      "flops_per_env_step": flops_step, "kernel": "step_kernel", "launch_ms": ms_step},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gb / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "frac": ach_gb / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_STEP},
         "peaks_measured": {"fp64_tflops": peaks["fp64"], "fp32_tflops": peaks["fp32"]},
         "rollout_fused": {"value": world * n * K / (ms_roll * 1e-3), "unit": UNIT, "ms_per_step": ms_roll / K,
