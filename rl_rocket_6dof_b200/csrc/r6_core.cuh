@@ -116,6 +116,11 @@ struct Tab {
     double AA[6][5];   // AA[s][j] = sum_k A[s][k] A[k][j]   : x_s = x + h C_s v + h^2 sum_j AA[s][j] dv_j
     double BA[6];      // BA[j]    = sum_k B[k] A[k][j]      : r_new = r + h v + h^2 sum_j BA[j] dv_j
     double EA[6];      // EA[j]    = sum_k E[k] A[k][j] + E[6] B[j] : e_r = h^2 sum_j EA[j] dv_j
+    // stage-input rows used by the rolled integrator: x = y + h * sum_j SA[row][j] K_j, positions
+    // r = r + h SC[row] v + h^2 sum_j SAA[row][j] dv_j.  rows 1..5 = (A, AA, C); row 6 = (B, BA, 1) gives
+    // y_new (the 7th Dormand-Prince stage is evaluated AT y_new); row 7 = (e_0, 0, 1) gives y + h f0,
+    // the probe point of select_initial_step.
+    double SA[8][6], SAA[8][6], SC[8];
     double P[7][4];
     double Psum[4];    // Psum[m]  = sum_j P[j][m]
     double PA[6][4];   // PA[j][m] = sum_k P[k][m] A[k][j] + P[6][m] B[j] : dense output of the position rows
@@ -165,6 +170,14 @@ constexpr Tab make_tab()
         t.BA[j] = b;
         t.EA[j] = e + E[6] * B[j];
     }
+    for (int s = 1; s < 6; s++) {
+        t.SC[s] = C[s];
+        for (int j = 0; j < 5; j++) { t.SA[s][j] = A[s][j]; t.SAA[s][j] = t.AA[s][j]; }
+    }
+    for (int j = 0; j < 6; j++) { t.SA[6][j] = B[j]; t.SAA[6][j] = t.BA[j]; }
+    t.SC[6] = 1;
+    t.SA[7][0] = 1;
+    t.SC[7] = 1;
     for (int m = 0; m < 4; m++) {
         double ps = 0;
         for (int j = 0; j < 7; j++) ps += P[j][m];
@@ -470,161 +483,201 @@ R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, ou
 }
 
 // ------------------------------------------------------------------------------------------------
+// x^(-1/5) for x > 0: the step-size controller's err^(-1/5) (rk.py:149-160) and the initial-step
+// (0.01/max(d1,d2))^(1/5) (common.py:129).  Device: single-precision seed from the MUFU log2/exp2
+// units, two Newton steps on y^-5 = x (quadratic: 1e-6 -> 1e-12 -> rounding).  Only the magnitude of
+// the NEXT step depends on it, so 3 ulp here move the solution by < 1e-18.
+R6_HD double inv_root5(double x)
+{
+#if defined(__CUDA_ARCH__)
+    const float xf = fminf(fmaxf(__double2float_rn(x), 1e-30f), 1e30f);
+    double y = (double)exp2f(-0.2f * __log2f(xf));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double y2 = y * y;
+        const double y5 = y2 * y2 * y;
+        y = fma(0.2 * y, fma(-x, y5, 1.0), y);
+    }
+    return y;
+#else
+    return exp(-0.2 * log(x));
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // solve_ivp(fun, [t, t+dt], y, events=height) with all defaults.  y in/out (quaternion NOT yet
 // re-normalised).  Returns the scipy status (0 / 1 / -1); natt = accepted + rejected RK attempts.
+//
+// Written as ONE loop around ONE right-hand-side evaluation: every RHS call of the algorithm — f0,
+// the probe f(y + h0 f0) of select_initial_step, the stages 2..6 of every attempt and f(y_new) — goes
+// through the same instructions, and what happens with the result is selected by `stage`.  The
+// evaluation point is always  y + h * sum_j SA[row][j] K_j  (rows of the extended tableau above), built
+// by one rolled loop.  This keeps the hot instruction footprint to a few KB (the instruction cache is
+// what the unrolled formulation was bound by) at the price of a switch per evaluation.
 template <bool kExact, class KS>
 R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS &K)
 {
     const Tab &T = R6_TAB_DYN;
     constexpr double rtol = 1e-3, atol = 1e-6;
     constexpr double inv_sqrt14 = 0.2672612419124244;   // 1/sqrt(14)
+    constexpr int kStageF0 = -1, kStageProbe = 0;        // stage >= 1: Dormand-Prince stage index (6 = f(y_new))
     const double t_bound = t + dt;
+    const double L = fabs(t_bound - t);                  // common.py:100 (interval length as SciPy computes it)
     const double w0 = y[10];
     density_setup(c, y[0]);
-    double h_abs;
-    {
-        const Deriv f = rhs_state<kExact>(c, y);                 // rk.py:96
-        k_store(K, 0, f);
-        // ---- select_initial_step (common.py:68-134), order 4 ----
-        const double L = fabs(t_bound - t);
-        double isc[14];
-        double s0 = 0, s1 = 0;
-#pragma unroll
-        for (int i = 0; i < 14; i++) {
-            isc[i] = fast_rcp(fma(fabs(y[i]), rtol, atol));
-            s0 += sq(y[i] * isc[i]);
-        }
-        const double fv[14] = {y[3], y[4], y[5], f.dv0, f.dv1, f.dv2, f.dq0, f.dq1, f.dq2, f.dq3, 0.0, f.dw1, f.dw2, c.dm};
-#pragma unroll
-        for (int i = 0; i < 14; i++) s1 += sq(fv[i] * isc[i]);
-        const double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        h0 = fmin(h0, L);
-        // f1 = RHS(y + h0 f0)
-        const Deriv f1 = rhs<kExact>(c, w0, y[0] + h0 * y[3], y[3] + h0 * f.dv0, y[4] + h0 * f.dv1, y[5] + h0 * f.dv2,
-                                     y[6] + h0 * f.dq0, y[7] + h0 * f.dq1, y[8] + h0 * f.dq2, y[9] + h0 * f.dq3,
-                                     y[11] + h0 * f.dw1, y[12] + h0 * f.dw2, y[13] + h0 * c.dm);
-        // (f1 - f0)/scale : position rows are h0*dv, the w0 and mass rows are 0
-        double s2 = sq(h0 * f.dv0 * isc[0]) + sq(h0 * f.dv1 * isc[1]) + sq(h0 * f.dv2 * isc[2]);
-        s2 += sq((f1.dv0 - f.dv0) * isc[3]) + sq((f1.dv1 - f.dv1) * isc[4]) + sq((f1.dv2 - f.dv2) * isc[5]);
-        s2 += sq((f1.dq0 - f.dq0) * isc[6]) + sq((f1.dq1 - f.dq1) * isc[7]) + sq((f1.dq2 - f.dq2) * isc[8]) +
-              sq((f1.dq3 - f.dq3) * isc[9]);
-        s2 += sq((f1.dw1 - f.dw1) * isc[11]) + sq((f1.dw2 - f.dw2) * isc[12]);
-        const double d2 = fast_sqrt(s2) * inv_sqrt14 / h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow_pos(0.01 / fmax(d1, d2), 0.2);
-        h_abs = fmin(fmin(100 * h0, h1), L);
-    }
+    // evaluation point (height, v, q, w1, w2, m) + the two horizontal positions of y_new
+    double xh = y[0], xv0 = y[3], xv1 = y[4], xv2 = y[5], xq0 = y[6], xq1 = y[7], xq2 = y[8], xq3 = y[9];
+    double xw1 = y[11], xw2 = y[12], xm = y[13], xr1 = y[1], xr2 = y[2];
+    int stage = kStageF0;
+    double h = 0, h_abs = 0, t_new = t;
     double g = y[0];
     int status = -2;
+    bool rejected = false;
     natt = 0;
-    while (status == -2) {
-        // ---- RungeKutta._step_impl (rk.py:111-176) ----
-        const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false, failed = false;
-        double t_new = t, h = 0;
-        double yn[14];
-        Deriv fn;
-        for (;;) {
-            if (h_abs < min_step) { failed = true; break; }
+    for (;;) {
+        const Deriv d = rhs<kExact>(c, w0, xh, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2, xm);
+        bool begin_attempt = false;
+        int row;
+        double hh;
+        if (stage >= 1 && stage <= 5) {
+            k_store(K, stage, d);
+            stage += 1;
+            row = stage; hh = h;
+        } else if (stage == 6) {
+            // ---- d = f(y_new): error estimate (rk.py:104-109, 141-142), accept / reject (rk.py:144-163) ----
+            double es[kNK], er[3];
+#pragma unroll
+            for (int i = 0; i < kNK; i++) es[i] = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) er[i] = 0;
+#pragma unroll 1
+            for (int j = 0; j < 6; j++) {
+                const double e = T.E[j], ea = T.EA[j];
+#pragma unroll
+                for (int i = 0; i < kNK; i++) {
+                    const double k = K.get(j, i);
+                    es[i] = fma(e, k, es[i]);
+                    if (i < 3) er[i] = fma(ea, k, er[i]);
+                }
+            }
+            const double e6 = T.E[6];
+            const double fnv[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
+            const double yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
+            const double yw[12] = {xh, xr1, xr2, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2};
+            const double h2 = h * h;
+            // the w0 and mass rows contribute exactly 0 to the error norm
+            double ssum = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const double sc = fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol);
+                const double e = (i < 3) ? h2 * er[i] : h * fma(e6, fnv[i - 3], es[i - 3]);
+                ssum += sq(e * fast_rcp(sc));
+            }
+            const double err = fast_sqrt(ssum) * inv_sqrt14;
+            const double raw = (err == 0) ? 10.0 : 0.9 * inv_root5(err);        // SAFETY * err^(-1/5)
+            if (err < 1) {
+                double factor = fmin(10.0, raw);
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                // accepted: ivp.py:659-699
+                const double t_old = t;
+                const double g_new = xh;
+                const bool ev = (g <= 0 && g_new >= 0) || (g >= 0 && g_new <= 0);
+                t = t_new;
+                if (t - t_bound >= 0) status = 0;
+                if (ev) {
+                    event_resolve(c, y, K, d, t_old, t_new);
+                    status = 1;
+                } else {
+                    y[0] = xh; y[1] = xr1; y[2] = xr2; y[3] = xv0; y[4] = xv1; y[5] = xv2;
+                    y[6] = xq0; y[7] = xq1; y[8] = xq2; y[9] = xq3; y[11] = xw1; y[12] = xw2; y[13] = xm;
+                }
+                if (status != -2) break;
+                k_store(K, 0, d);                                   // first-same-as-last
+                g = g_new;
+                rejected = false;
+            } else {
+                h_abs *= fmax(0.2, raw);
+                rejected = true;
+            }
+            begin_attempt = true;
+        } else if (stage == kStageF0) {
+            // ---- d = f0 (rk.py:96); select_initial_step part 1 (common.py:105-119), order 4 ----
+            k_store(K, 0, d);
+            double s0 = 0, s1 = 0;
+            const double fv[14] = {y[3], y[4], y[5], d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, 0.0, d.dw1, d.dw2, c.dm};
+#pragma unroll
+            for (int i = 0; i < 14; i++) {
+                const double isc = fast_rcp(fma(fabs(y[i]), rtol, atol));
+                s0 += sq(y[i] * isc);
+                s1 += sq(fv[i] * isc);
+            }
+            const double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 * fast_rcp(d1);
+            h0 = fmin(h0, L);
+            h = h0;            // probe step; d1 is parked in h_abs until the probe comes back
+            h_abs = d1;
+            stage = kStageProbe;
+            row = 7; hh = h0;
+        } else {
+            // ---- d = f(y + h0 f0); select_initial_step part 2 (common.py:121-134) ----
+            const double h0 = h, d1 = h_abs;
+            // (f1 - f0)/scale: position rows are h0*dv, the w0 and mass rows are 0
+            const double f0v[kNK] = {K.get(0, 0), K.get(0, 1), K.get(0, 2), K.get(0, 3), K.get(0, 4), K.get(0, 5),
+                                     K.get(0, 6), K.get(0, 7), K.get(0, 8)};
+            const double f1v[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
+            const double yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
+            double s2 = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const double isc = fast_rcp(fma(fabs(yo[i]), rtol, atol));
+                const double e = (i < 3) ? h0 * f0v[i] : f1v[i - 3] - f0v[i - 3];
+                s2 += sq(e * isc);
+            }
+            const double d2 = fast_sqrt(s2) * inv_sqrt14 * fast_rcp(h0);
+            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_root5(100.0 * fmax(d1, d2));
+            h_abs = fmin(fmin(100 * h0, h1), L);
+            begin_attempt = true;
+        }
+        if (begin_attempt) {
+            // ---- RungeKutta._step_impl entry (rk.py:111-131) ----
+            const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+            if (h_abs < min_step) {
+                if (rejected) { status = -1; break; }
+                h_abs = min_step;
+            }
             t_new = t + h_abs;
             if (t_new - t_bound > 0) t_new = t_bound;
             h = t_new - t;
             h_abs = fabs(h);
             natt++;
-            const double h2 = h * h;
-            // ---- rk_step (rk.py:14-71): stages 2..6, rolled; position rows via the AA tableau ----
-#pragma unroll 1
-            for (int s = 1; s < 6; s++) {
-                double acc[kNK], ax = 0;
-#pragma unroll
-                for (int i = 0; i < kNK; i++) acc[i] = 0;
-#pragma unroll 1
-                for (int j = 0; j < s; j++) {
-                    const double a = T.A[s][j], aa = T.AA[s][j];
-                    const double k0 = K.get(j, 0);
-                    acc[0] = fma(a, k0, acc[0]);
-                    ax = fma(aa, k0, ax);
-#pragma unroll
-                    for (int i = 1; i < kNK; i++) acc[i] = fma(a, K.get(j, i), acc[i]);
-                }
-                const double hc = h * T.C[s];
-                const Deriv d = rhs<kExact>(c, w0, fma(h2, ax, fma(hc, y[3], y[0])),
-                                            fma(h, acc[0], y[3]), fma(h, acc[1], y[4]), fma(h, acc[2], y[5]),
-                                            fma(h, acc[3], y[6]), fma(h, acc[4], y[7]), fma(h, acc[5], y[8]),
-                                            fma(h, acc[6], y[9]), fma(h, acc[7], y[11]), fma(h, acc[8], y[12]),
-                                            fma(hc, c.dm, y[13]));
-                k_store(K, s, d);
-            }
-            // ---- y_new and the stage part of the error estimate (rk.py:66, 104-105) ----
-            double bs[kNK], es[kNK], br[3], er[3];
-#pragma unroll
-            for (int i = 0; i < kNK; i++) { bs[i] = 0; es[i] = 0; }
-#pragma unroll
-            for (int i = 0; i < 3; i++) { br[i] = 0; er[i] = 0; }
-#pragma unroll 1
-            for (int j = 0; j < 6; j++) {
-                const double b = T.B[j], e = T.E[j], ba = T.BA[j], ea = T.EA[j];
-#pragma unroll
-                for (int i = 0; i < kNK; i++) {
-                    const double k = K.get(j, i);
-                    bs[i] = fma(b, k, bs[i]);
-                    es[i] = fma(e, k, es[i]);
-                    if (i < 3) { br[i] = fma(ba, k, br[i]); er[i] = fma(ea, k, er[i]); }
-                }
-            }
-            yn[0] = fma(h2, br[0], fma(h, y[3], y[0]));
-            yn[1] = fma(h2, br[1], fma(h, y[4], y[1]));
-            yn[2] = fma(h2, br[2], fma(h, y[5], y[2]));
-            yn[3] = fma(h, bs[0], y[3]); yn[4] = fma(h, bs[1], y[4]); yn[5] = fma(h, bs[2], y[5]);
-            yn[6] = fma(h, bs[3], y[6]); yn[7] = fma(h, bs[4], y[7]); yn[8] = fma(h, bs[5], y[8]); yn[9] = fma(h, bs[6], y[9]);
-            yn[10] = w0;
-            yn[11] = fma(h, bs[7], y[11]); yn[12] = fma(h, bs[8], y[12]);
-            yn[13] = fma(h, c.dm, y[13]);
-            fn = rhs_state<kExact>(c, yn);                        // K[6] = f_new (rk.py:67-69)
-            const double e6 = T.E[6];
-            const double fnv[kNK] = {fn.dv0, fn.dv1, fn.dv2, fn.dq0, fn.dq1, fn.dq2, fn.dq3, fn.dw1, fn.dw2};
-            // error norm (rk.py:107-109, 141-142); the w0 and mass rows contribute exactly 0
-            double ssum = 0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), rtol, atol);
-                ssum += sq(h2 * er[i] * fast_rcp(sc));
-            }
-            const int comp[kNK] = {3, 4, 5, 6, 7, 8, 9, 11, 12};
-#pragma unroll
-            for (int i = 0; i < kNK; i++) {
-                const int ci = comp[i];
-                const double sc = fma(fmax(fabs(y[ci]), fabs(yn[ci])), rtol, atol);
-                ssum += sq(h * fma(e6, fnv[i], es[i]) * fast_rcp(sc));
-            }
-            const double err = fast_sqrt(ssum) * inv_sqrt14;
-            const double raw = (err == 0) ? 10.0 : 0.9 * pow_pos(err, -0.2);   // SAFETY * err^(-1/5)
-            if (err < 1) {
-                double factor = fmin(10.0, raw);
-                if (rejected) factor = fmin(1.0, factor);
-                h_abs *= factor;
-                break;
-            }
-            h_abs *= fmax(0.2, raw);
-            rejected = true;
+            stage = 1;
+            row = 1; hh = h;
         }
-        if (failed) { status = -1; break; }
-        // accepted: ivp.py:659-699
-        const double t_old = t;
-        const double g_new = yn[0];
-        const bool ev = (g <= 0 && g_new >= 0) || (g >= 0 && g_new <= 0);
-        t = t_new;
-        if (t - t_bound >= 0) status = 0;
-        if (ev) {
-            event_resolve(c, y, K, fn, t_old, t_new);
-            status = 1;
-        } else {
+        // ---- evaluation point of the next RHS call: rk_step (rk.py:58-66) with the row's coefficients ----
+        {
+            double acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
 #pragma unroll
-            for (int i = 0; i < 14; i++) y[i] = yn[i];
-            if (status == -2) k_store(K, 0, fn);                  // first-same-as-last
+            for (int i = 0; i < kNK; i++) acc[i] = 0;
+            const int cnt = row < 6 ? row : (row == 6 ? 6 : 1);
+#pragma unroll 1
+            for (int j = 0; j < cnt; j++) {
+                const double a = T.SA[row][j], aa = T.SAA[row][j];
+                const double k0 = K.get(j, 0), k1 = K.get(j, 1), k2 = K.get(j, 2);
+                acc[0] = fma(a, k0, acc[0]); acc[1] = fma(a, k1, acc[1]); acc[2] = fma(a, k2, acc[2]);
+                ar0 = fma(aa, k0, ar0); ar1 = fma(aa, k1, ar1); ar2 = fma(aa, k2, ar2);
+#pragma unroll
+                for (int i = 3; i < kNK; i++) acc[i] = fma(a, K.get(j, i), acc[i]);
+            }
+            const double hc = hh * T.SC[row], hh2 = hh * hh;
+            xh = fma(hh2, ar0, fma(hc, y[3], y[0]));
+            xr1 = fma(hh2, ar1, fma(hc, y[4], y[1]));
+            xr2 = fma(hh2, ar2, fma(hc, y[5], y[2]));
+            xv0 = fma(hh, acc[0], y[3]); xv1 = fma(hh, acc[1], y[4]); xv2 = fma(hh, acc[2], y[5]);
+            xq0 = fma(hh, acc[3], y[6]); xq1 = fma(hh, acc[4], y[7]); xq2 = fma(hh, acc[5], y[8]); xq3 = fma(hh, acc[6], y[9]);
+            xw1 = fma(hh, acc[7], y[11]); xw2 = fma(hh, acc[8], y[12]);
+            xm = fma(hc, c.dm, y[13]);
         }
-        g = g_new;
     }
     return status;
 }
