@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 4
+#define R6_ABI_VERSION 5
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -153,12 +153,17 @@ int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset
             const float *actions, uint64_t seed, void *stream);
 
 /*
- * k fused env-steps per launch with the state held in registers (auto-reset always on).
+ * k fused env-steps per launch with the state held in registers.
  * mode R6_ACT_PHILOX: action = uniform(-1,1) from (seed, global env id, step_base + j);
- * mode R6_ACT_MLP:    action = clip(actor(obs[0:13]), -1, 1) (evaluate_policy, deterministic);
+ * mode R6_ACT_MLP:    action = clip(actor(obs[0:13]), -1, 1), the deterministic SB3 MlpPolicy forward
+ *                     (float32, weights staged in shared memory) — evaluate_policy of
+ *                     montecarlo_script.py:57-64 with the policy inside the kernel;
  * mode R6_ACT_BUFFER: action = act_buf[j][i][:].
+ * p->auto_reset != 0: finished envs restart inside the kernel (VecEnv semantics).
+ * p->auto_reset == 0: one episode per env — an env that finishes keeps done = 1, its terminal
+ *                     state / observation / ep_info, and is skipped by later launches until r6_reset.
  * traj_* (nullable) record the rollout: obs [k][13][n] (observation the action was computed
- * from), act [k][n][3], rew [k][n] float32, done [k][n] uint8.
+ * from), act [k][n][3], rew [k][n] float32, done [k][n] uint8 (2 = padding after a frozen env's end).
  */
 int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, int32_t k,
                int32_t mode, const R6Mlp *mlp, const float *act_buf, uint64_t seed,

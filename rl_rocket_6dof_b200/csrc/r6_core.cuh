@@ -1028,6 +1028,84 @@ R6_HD void philox_action(uint64_t seed, uint64_t genv, uint64_t step, float &a0,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Deterministic SB3 MlpPolicy actor (PPO "MlpPolicy", net_arch [128, 64], tanh; the network of
+// best_model_*.zip that montecarlo_script.py:54-64 evaluates):
+//     a = clip(W2 tanh(W1 tanh(W0 x + b0) + b1) + b2, -1, 1),   x = obs[0:13] (RemoveMassFromObs)
+// all in float32 like torch.  Packed weight block (floats), built once per CTA in shared memory
+// (or by the host build in plain memory):
+//     [0, 2048)        W0 rows padded to 16: row j = (w0[j][0..12], b0[j], 0, 0)
+//     [2048, 10240)    W1 transposed: [in j][out k]  (64 contiguous floats per hidden-0 unit)
+//     [10240, 10304)   b1      [10304, 10496)  W2 [3][64]      [10496, 10500)  b2 (+ pad)
+// One thread evaluates the whole network for its environment: hidden-0 units are produced one at a
+// time and immediately scattered into the 64 hidden-1 accumulators, so nothing but those 64 floats
+// is live; every weight read is a warp-uniform (broadcast) 16-byte load.
+constexpr int kMlpIn = 13, kMlpH0 = 128, kMlpH1 = 64, kMlpOut = 3;
+constexpr int kMlpOffW1 = kMlpH0 * 16, kMlpOffB1 = kMlpOffW1 + kMlpH0 * kMlpH1, kMlpOffW2 = kMlpOffB1 + kMlpH1;
+constexpr int kMlpOffB2 = kMlpOffW2 + kMlpOut * kMlpH1, kMlpFloats = kMlpOffB2 + 4;
+
+struct F4 { float x, y, z, w; };
+R6_HD F4 ld4(const float *p)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return F4{v.x, v.y, v.z, v.w};
+#else
+    return F4{p[0], p[1], p[2], p[3]};
+#endif
+}
+
+// element `idx` of the packed block from the SB3-layout tensors ([out][in] row-major)
+R6_HD float mlp_pack_element(const R6Mlp &m, int idx)
+{
+    if (idx < kMlpOffW1) {
+        const int j = idx >> 4, i = idx & 15;
+        return i < kMlpIn ? m.w0[j * kMlpIn + i] : (i == kMlpIn ? m.b0[j] : 0.0f);
+    }
+    if (idx < kMlpOffB1) {
+        const int r = idx - kMlpOffW1, j = r / kMlpH1, k = r % kMlpH1;
+        return m.w1[k * kMlpH0 + j];
+    }
+    if (idx < kMlpOffW2) return m.b1[idx - kMlpOffB1];
+    if (idx < kMlpOffB2) return m.w2[idx - kMlpOffW2];
+    return idx - kMlpOffB2 < kMlpOut ? m.b2[idx - kMlpOffB2] : 0.0f;
+}
+
+R6_HD void mlp_policy(const float *W, const float *x, float &a0, float &a1, float &a2)
+{
+    float acc[kMlpH1];
+#pragma unroll
+    for (int k = 0; k < kMlpH1; k++) acc[k] = 0.0f;
+#pragma unroll 2
+    for (int j = 0; j < kMlpH0; j++) {
+        const F4 wa = ld4(W + j * 16), wb = ld4(W + j * 16 + 4), wc = ld4(W + j * 16 + 8), wd = ld4(W + j * 16 + 12);
+        float s = wa.x * x[0];
+        s = f32_fma(wa.y, x[1], s); s = f32_fma(wa.z, x[2], s); s = f32_fma(wa.w, x[3], s);
+        s = f32_fma(wb.x, x[4], s); s = f32_fma(wb.y, x[5], s); s = f32_fma(wb.z, x[6], s); s = f32_fma(wb.w, x[7], s);
+        s = f32_fma(wc.x, x[8], s); s = f32_fma(wc.y, x[9], s); s = f32_fma(wc.z, x[10], s); s = f32_fma(wc.w, x[11], s);
+        s = f32_fma(wd.x, x[12], s);
+        const float h = tanhf(s + wd.y);
+        const float *w1 = W + kMlpOffW1 + j * kMlpH1;
+#pragma unroll
+        for (int k = 0; k < kMlpH1; k += 4) {
+            const F4 w = ld4(w1 + k);
+            acc[k] = f32_fma(w.x, h, acc[k]); acc[k + 1] = f32_fma(w.y, h, acc[k + 1]);
+            acc[k + 2] = f32_fma(w.z, h, acc[k + 2]); acc[k + 3] = f32_fma(w.w, h, acc[k + 3]);
+        }
+    }
+    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMlpH1; k++) {
+        const float h = tanhf(acc[k] + W[kMlpOffB1 + k]);
+        o0 = f32_fma(W[kMlpOffW2 + k], h, o0);
+        o1 = f32_fma(W[kMlpOffW2 + kMlpH1 + k], h, o1);
+        o2 = f32_fma(W[kMlpOffW2 + 2 * kMlpH1 + k], h, o2);
+    }
+    a0 = fminf(fmaxf(o0 + W[kMlpOffB2], -1.0f), 1.0f);
+    a1 = fminf(fmaxf(o1 + W[kMlpOffB2 + 1], -1.0f), 1.0f);
+    a2 = fminf(fmaxf(o2 + W[kMlpOffB2 + 2], -1.0f), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Registers carried by the thread that owns an environment, and the glue of one env step
 struct Env {
     double y[14];

@@ -41,6 +41,7 @@ constexpr int kThreads = R6_THREADS;
 #define R6_MIN_BLOCKS 3          /* resident CTAs per SM the register allocation is tuned for */
 #endif
 constexpr int kSmemBytes = 6 * r6::kNK * kThreads * (int)sizeof(double);   // stage storage, 55,296 B per CTA
+constexpr int kSmemMlpBytes = kSmemBytes + r6::kMlpFloats * (int)sizeof(float);   // + packed policy weights (42,000 B)
 
 using namespace r6;
 using KStore = KShared<kThreads>;
@@ -129,6 +130,7 @@ reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, i
     env_reset(p, b, seed, env_offset + i, e);
     env_store(b, n, i, e);
     write_obs(b.obs, n, i, p, dv, e.y);
+    if (b.done) b.done[i] = 0;          // un-freezes the env for one-episode (auto_reset = 0) rollouts
 }
 
 template <bool kExact>
@@ -174,19 +176,31 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     if (b.stats) stats_flush(st, b.stats);
 }
 
-// k fused steps, state in registers; actions from Philox or a [k][n][3] buffer.
+// k fused steps, state in registers; actions from Philox, a [k][n][3] buffer or the fused policy MLP.
+// p.auto_reset != 0: finished envs restart (VecEnv semantics).  p.auto_reset == 0: an env that finishes
+// is left frozen with done = 1 and its terminal state / observation recorded (evaluate_policy /
+// Monte-Carlo semantics: one episode per env), and is skipped by later launches until r6_reset.
 template <int kMode, bool kExact>
-__global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, kMode == R6_ACT_MLP ? 2 : R6_MIN_BLOCKS)   // MLP: weights take the 3rd CTA's smem
 rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, int k_steps,
-               const float *__restrict__ act_buf, uint64_t seed, int64_t step_base, float *traj_obs, float *traj_act,
-               float *traj_rew, uint8_t *traj_done)
+               const float *__restrict__ act_buf, const R6Mlp mlp, uint64_t seed, int64_t step_base, float *traj_obs,
+               float *traj_act, float *traj_rew, uint8_t *traj_done)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     KStore K = make_kstore();
+    const float *W = nullptr;
+    if (kMode == R6_ACT_MLP) {
+        // pack the policy weights into shared memory once per CTA (transposes W1, pads W0 rows)
+        extern __shared__ double r6_smem[];
+        float *Ws = reinterpret_cast<float *>(r6_smem + 6 * kNK * kThreads);
+        for (int idx = threadIdx.x; idx < kMlpFloats; idx += kThreads) Ws[idx] = mlp_pack_element(mlp, idx);
+        __syncthreads();
+        W = Ws;
+    }
     StatAcc st;
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
-    if (i < n) {
+    if (i < n && (p.auto_reset || b.done[i] == 0)) {
         Env e;
         env_load(b, n, i, e);
         StepOut o;
@@ -195,7 +209,12 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
         for (int j = 0; j < k_steps; j++) {
             float a0, a1, a2;
             if (kMode == R6_ACT_PHILOX) philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)(step_base + j), a0, a1, a2);
-            else {
+            else if (kMode == R6_ACT_MLP) {
+                float x[kMlpIn];
+#pragma unroll
+                for (int c = 0; c < kMlpIn; c++) x[c] = obs_component(p, dv, e.y, c);
+                mlp_policy(W, x, a0, a1, a2);
+            } else {
                 const float *a = act_buf + ((int64_t)j * n + i) * 3;
                 a0 = a[0]; a1 = a[1]; a2 = a[2];
             }
@@ -209,12 +228,18 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
             if (traj_done) traj_done[(int64_t)j * n + i] = o.finished ? 1 : 0;
             stats_add(st, o, e);
             if (o.finished) {
-                if (j == k_steps - 1) {
-                    write_obs(b.terminal_obs, n, i, p, dv, e.y);
+                write_obs(b.terminal_obs, n, i, p, dv, e.y);
 #pragma unroll
-                    for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
-                }
+                for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
                 if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+                if (!p.auto_reset) {
+                    // frozen: the rest of the trajectory record (if any) is padding
+                    for (int jj = j + 1; jj < k_steps; jj++) {
+                        if (traj_rew) traj_rew[(int64_t)jj * n + i] = 0.0f;
+                        if (traj_done) traj_done[(int64_t)jj * n + i] = 2;
+                    }
+                    break;
+                }
                 env_reset(p, b, seed, env_offset + i, e);
             }
         }
@@ -280,9 +305,9 @@ __global__ void __launch_bounds__(256) peak_fma_kernel(int iters, double *sink)
 
 // kernels that keep the RK stages in dynamic shared memory need the > 48 KB opt-in once per process
 template <class F>
-int enable_smem(F kernel)
+int enable_smem(F kernel, int bytes = kSmemBytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return fail(R6_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return R6_OK;
 }
@@ -299,6 +324,8 @@ int ensure_attributes()
     rc |= enable_smem(rollout_kernel<R6_ACT_PHILOX, true>);
     rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, false>);
     rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, true>);
+    rc |= enable_smem(rollout_kernel<R6_ACT_MLP, false>, kSmemMlpBytes);
+    rc |= enable_smem(rollout_kernel<R6_ACT_MLP, true>, kSmemMlpBytes);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -374,16 +401,21 @@ int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_off
     const Derived dv = make_derived(*p);
     const unsigned g = (unsigned)blocks_for(n);
     cudaStream_t s = (cudaStream_t)stream;
-    (void)mlp;
     const bool exact = !(p->dt <= kMaxDtSeries);
-#define R6_LAUNCH_ROLLOUT(MODE, EXACT, BUF)                                                                         \
-    rollout_kernel<MODE, EXACT><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, k, BUF, seed, step_base, \
-                                                                traj_obs, traj_act, traj_rew, traj_done)
+    R6Mlp m{};
+#define R6_LAUNCH_ROLLOUT(MODE, EXACT, BUF, SMEM)                                                                \
+    rollout_kernel<MODE, EXACT><<<g, kThreads, SMEM, s>>>(*p, *b, dv, n, env_offset, k, BUF, m, seed, step_base, \
+                                                          traj_obs, traj_act, traj_rew, traj_done)
     if (mode == R6_ACT_PHILOX) {
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, true, nullptr); else R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, false, nullptr);
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, true, nullptr, kSmemBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, false, nullptr, kSmemBytes);
     } else if (mode == R6_ACT_BUFFER) {
         if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf);
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf, kSmemBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf, kSmemBytes);
+    } else if (mode == R6_ACT_MLP) {
+        if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
+            return fail(R6_EINVAL, "policy weights are null%s");
+        m = *mlp;
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_MLP, true, nullptr, kSmemMlpBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_MLP, false, nullptr, kSmemMlpBytes);
     } else
         return fail(R6_EINVAL, "unsupported action mode%s");
 #undef R6_LAUNCH_ROLLOUT

@@ -45,6 +45,8 @@ def lib():
         L.hs_euler_tests.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_int)] * 2
         L.hs_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         L.hs_philox_action.argtypes = [C.c_uint64] * 3 + [C.c_void_p]
+        L.hs_mlp_pack.argtypes = [C.c_void_p, C.c_void_p]
+        L.hs_mlp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -72,3 +74,17 @@ class HostSimBatch:
         lib().hs_step(C.byref(self.p), self.t_table.ctypes.data, self.envs.ctypes.data, self.n, a.ctypes.data,
                       self.outs.ctypes.data)
         return self.outs
+
+
+def mlp_actions(weights, obs13):
+    """Fused-policy network of the kernels (host build) on packed weights: obs [n,13] f32 -> actions [n,3]."""
+    from rl_rocket_6dof_b200._lib import R6Mlp
+    L = lib()
+    w = {k: np.ascontiguousarray(v, np.float32) for k, v in weights.items()}
+    m = R6Mlp(*[w[k].ctypes.data for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+    W = np.zeros(L.hs_mlp_floats(), np.float32)
+    L.hs_mlp_pack(C.byref(m), W.ctypes.data)
+    x = np.ascontiguousarray(obs13, np.float32).reshape(-1, 13)
+    out = np.zeros((len(x), 3), np.float32)
+    L.hs_mlp(W.ctypes.data, x.ctypes.data, len(x), out.ctypes.data)
+    return out

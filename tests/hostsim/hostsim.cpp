@@ -92,6 +92,14 @@ void hs_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, 
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+// fused-policy network on packed weights (W has kMlpFloats floats, built with mlp_pack_element)
+int hs_mlp_floats(void) { return kMlpFloats; }
+void hs_mlp_pack(const R6Mlp *m, float *W) { for (int i = 0; i < kMlpFloats; i++) W[i] = mlp_pack_element(*m, i); }
+void hs_mlp(const float *W, const float *obs13, int64_t n, float *actions)
+{
+    for (int64_t i = 0; i < n; i++) mlp_policy(W, obs13 + 13 * i, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2]);
+}
+
 void hs_philox_action(uint64_t seed, uint64_t genv, uint64_t step, float a[3]) { philox_action(seed, genv, step, a[0], a[1], a[2]); }
 
 }  // extern "C"

@@ -1,0 +1,118 @@
+"""Closed-loop path on the GPU: policy MLP fused into the rollout kernel (R6_ACT_MLP), one-episode
+(auto_reset = 0) semantics and the Monte-Carlo dispersion driver, against the closed-loop run the
+unmodified reference produced with best_model_2bo71j9m (tests/golden/policy_cl.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from parity_utils import env_params, f32_ulp_diff
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_cl.npz")
+
+
+def _golden_episodes(g):
+    starts = [int(s) for s in g["ic_step"]]
+    ends = starts[1:] + [len(g["action"])]
+    return starts, ends
+
+
+def test_fused_mlp_actions_match_recorded():
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts = set(int(s) for s in g["ic_step"])
+    idx = np.array([k for k in range(1, len(g["action"])) if k not in starts])
+    n = len(idx)
+    ep = env_params()
+    env = Rocket6DOFBatch(n, params=ep, device="cuda:0", auto_reset=True, seed=3)
+    st = g["state"][idx - 1]
+    env.set_state(torch.from_numpy(st.astype(np.float32)))
+    env.state.copy_(torch.from_numpy(np.ascontiguousarray(st.T)))       # the float64 state the policy saw
+    traj = env.rollout(1, ACT_MLP, mlp=policy.to_device(w, env.device), record=True)
+    torch.cuda.synchronize()
+    a = traj["act"][0].cpu().numpy()
+    assert np.abs(a - g["action"][idx]).max() <= 2e-6
+    obs = traj["obs"][0].t().cpu().numpy()
+    assert f32_ulp_diff(obs, g["obs"][idx - 1][:, :13]).max() <= 1.0
+
+
+def test_rollout_mlp_needs_weights():
+    from rl_rocket_6dof_b200._lib import R6Error
+    from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
+    env = Rocket6DOFBatch(8, params=env_params(), device="cuda:0")
+    env.reset()
+    with pytest.raises(ValueError):
+        env.rollout(1, ACT_MLP)
+    import ctypes as C
+    rc = env.lib.r6_rollout(C.byref(env._p), C.byref(env._b), 8, 0, 1, ACT_MLP, None, None, 0, 0, None, None, None,
+                            None, None)
+    assert rc == -1 and b"policy weights" in env.lib.r6_last_error()
+    assert R6Error is not None
+
+
+def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path):
+    """30 episodes from the reference's own initial conditions, policy in the loop on both sides.
+    The loop feeds a float32 network back into the dynamics, so agreement is to the amplification of
+    float32 round-off in the actions (SURVEY §7 hard part 8), not to 1e-9: episode lengths within one
+    step, terminal states within 2e-3 of the normaliser, dispersion means within 1 %."""
+    from rl_rocket_6dof_b200 import montecarlo, policy
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts, ends = _golden_episodes(g)
+    n = len(starts)
+    assert g["done"][ends[-1] - 1] or g["truncated"][ends[-1] - 1]
+    csv_path = str(tmp_path / "results_montecarlo.csv")
+    res = montecarlo.run_montecarlo(n, w, device="cuda:0", ic_table=g["ic"], csv_path=csv_path, chunk_steps=64)
+    ref_len = np.array([e - s for s, e in zip(starts, ends)])
+    ref_term = np.stack([g["state"][e - 1] for e in ends])
+    print("episode length diff:", res["episode_length"] - ref_len)
+    assert np.abs(res["episode_length"] - ref_len).max() <= 1
+    norm = env_params().state_normalizer
+    err = np.abs(res["terminal_state"] - ref_term) / norm
+    print("terminal state error / normaliser: max", err.max(0))
+    same = res["episode_length"] == ref_len
+    assert same.mean() >= 0.8
+    assert err[same].max() <= 2e-3
+    # dispersion statistics (what montecarlo_script.py prints)
+    ref_cols = {
+        "final_position_error": np.linalg.norm(ref_term[:, 0:3], axis=1),
+        "final_velocity_error": np.linalg.norm(ref_term[:, 3:6], axis=1),
+        "attitude_error": 0.5 * np.rad2deg(np.arccos(ref_term[:, 6])),
+        "angular_velocity_error": np.linalg.norm(ref_term[:, 10:13], axis=1),
+        "used mass": ref_term[:, 13],
+    }
+    for k, v in ref_cols.items():
+        assert abs(res["mean"][k] - v.mean()) <= 0.01 * abs(v.mean()) + 1e-6, k
+        assert abs(res["std"][k] - v.std(ddof=1)) <= 0.05 * abs(v.std(ddof=1)) + 1e-6, k
+    rows = open(csv_path).read().strip().splitlines()
+    assert rows[0].split(",") == montecarlo.HEADER and len(rows) == n + 1
+    assert "final_position_error has mean" in montecarlo.format_report(res)
+    assert res["stats"]["episodes"] == n
+
+
+def test_one_episode_rollout_freezes_finished_envs():
+    import torch
+    from rl_rocket_6dof_b200.batch import ACT_PHILOX, Rocket6DOFBatch
+    n = 512
+    env = Rocket6DOFBatch(n, params=env_params(), device="cuda:0", auto_reset=False, seed=11)
+    env.reset()
+    for _ in range(8):
+        env.rollout(64, ACT_PHILOX)
+    torch.cuda.synchronize()
+    assert bool(env.done.all())                     # random-action episodes last 99-211 steps
+    s = env.stats.cpu().numpy()
+    assert s[0] == n and s[7] == s[2]               # one episode per env; steps == sum of lengths
+    snap = (env.state.clone(), env.terminal_state.clone(), env.step_count.clone(), env.stats.clone())
+    env.rollout(64, ACT_PHILOX)
+    torch.cuda.synchronize()
+    for a, b in zip(snap, (env.state, env.terminal_state, env.step_count, env.stats)):
+        assert torch.equal(a, b)
+    assert torch.equal(env.state, env.terminal_state)
+    env.reset()                                     # un-freezes
+    env.rollout(4, ACT_PHILOX)
+    torch.cuda.synchronize()
+    assert int(env.step_count.min()) == 4 and not bool(env.done.any())
