@@ -264,6 +264,27 @@ def run_b200(args):
     ms_roll = max_over_ranks(e0.elapsed_time(e1))
     barrier()
 
+    # ---- fixed-policy closed loop: SB3 MlpPolicy actor fused into the rollout kernel ----------
+    from rl_rocket_6dof_b200 import policy as _policy
+    from rl_rocket_6dof_b200.batch import ACT_MLP
+    wpath = os.path.join(ROOT, "tests", "golden", "policy_cl.npz")
+    if os.path.exists(wpath):
+        wts, wsrc = _policy.load_npz(wpath), "best_model_2bo71j9m actor (tests/golden/policy_cl.npz)"
+    else:
+        g0 = np.random.default_rng(0)
+        wts = {k: (g0.standard_normal(shp) * 0.1).astype(np.float32) for k, shp in _policy.SHAPES.items()}
+        wsrc = "random-init actor of the same architecture"
+    wdev = _policy.to_device(wts, dev)
+    KP = max(K // 2, 1)
+    env.rollout(KP, ACT_MLP, mlp=wdev)
+    barrier()
+    e0.record(stream)
+    env.rollout(KP, ACT_MLP, mlp=wdev)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_pol = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+
     # ---- end to end through the VecEnv fast path (host actions in, host obs/reward/done out) --
     for w in range(W):
         vec.step_host(acts_h[w % R])
@@ -327,6 +348,9 @@ def run_b200(args):
         "peaks_measured": {"fp64_tflops": peaks["fp64"], "fp32_tflops": peaks["fp32"]},
         "rollout_fused": {"value": world * n * K / (ms_roll * 1e-3), "unit": UNIT, "ms_per_step": ms_roll / K,
                           "launches": 1, "actions": "in-kernel Philox4x32-10"},
+        "rollout_policy": {"value": world * n * KP / (ms_pol * 1e-3), "unit": UNIT, "ms_per_step": ms_pol / KP,
+                           "launches": 1, "actions": "fused MlpPolicy 13-128-64-3 tanh, fp32, deterministic",
+                           "weights": wsrc},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},

@@ -10,7 +10,10 @@
  * Conventions
  *  - plain C: pointers + sizes, no torch / C++ types.  Every buffer pointer is DEVICE memory owned
  *    by the caller (a torch CUDA tensor's data_ptr()); the library allocates nothing and keeps
- *    no global state except a thread-local error string.
+ *    no global state except a thread-local error string.  The per-step OUTPUT arrays (obs, reward,
+ *    reward_f32, done, flags) and `actions` may instead point at pinned, device-mapped HOST memory
+ *    (cudaHostAlloc / torch pin_memory): the kernel then streams them over PCIe itself, overlapped
+ *    with the computation, and no separate copy is needed (Rocket6DOFVecEnv.step_host).
  *  - every call enqueues work on the caller's stream (`cudaStream_t` passed as void*) and returns
  *    without synchronising; results are valid after the stream is synchronised.
  *  - return value: 0 on success, negative R6_E* on error; r6_last_error() has the text.
@@ -88,7 +91,8 @@ typedef struct R6Params {
     int32_t clip_reward;        /* apply ClipReward(clip_lo, clip_hi) to reward[] */
     int32_t auto_reset;         /* VecEnv semantics: reset finished envs inside the step */
     int32_t n_t;                /* entries in R6Buffers.t_table */
-    int32_t reserved;
+    int32_t obs_rows;           /* rows of obs[] / terminal_obs[] the kernels write: 0 or 14 = all, 13 = RemoveMassFromObs
+                                   (saves the mass row when obs[] is mapped host memory) */
 } R6Params;
 
 /* Device pointers. n = number of local envs. Nullable members are marked. */
@@ -102,7 +106,7 @@ typedef struct R6Buffers {
     double *ep_return;      /* [n] running sum of reward[] over the episode (Monitor "r") */
     /* per-step outputs */
     float *obs;             /* [14][n] (row 13 = mass/normalizer; RemoveMassFromObs = rows 0..12) */
-    double *reward;         /* [n] */
+    double *reward;         /* [n] nullable when reward_f32 is given */
     uint8_t *done;          /* [n] done OR truncated (what a VecEnv reports) */
     uint8_t *flags;         /* [n] R6_F_* */
     float *terminal_obs;    /* [14][n] obs of the last step of a finished episode ("terminal_observation") */

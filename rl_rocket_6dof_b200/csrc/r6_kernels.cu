@@ -99,8 +99,10 @@ __device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t
 __device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, const R6Params &p, const Derived &dv,
                                           const double *y)
 {
+    const int rows = p.obs_rows > 0 ? p.obs_rows : 14;
 #pragma unroll
-    for (int c = 0; c < 14; c++) obs[(int64_t)c * n + i] = obs_component(p, dv, y, c);   // rocket_env.py:503-504
+    for (int c = 0; c < 14; c++)
+        if (c < rows) obs[(int64_t)c * n + i] = obs_component(p, dv, y, c);   // rocket_env.py:503-504
 }
 
 __device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const Env &e)
@@ -149,7 +151,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
         StepOut o;
         env_step<kExact>(p, dv, b.t_table, e, a0, a1, a2, o, K);
-        b.reward[i] = o.reward;
+        if (b.reward) b.reward[i] = o.reward;
         if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
         b.flags[i] = (uint8_t)o.flags;
@@ -243,7 +245,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
                 env_reset(p, b, seed, env_offset + i, e);
             }
         }
-        b.reward[i] = o.reward;
+        if (b.reward) b.reward[i] = o.reward;
         if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
         b.flags[i] = (uint8_t)o.flags;
@@ -347,7 +349,7 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
 {
     int rc = validate(p, b, n);
     if (rc) return rc;
-    if (!b->reward || !b->done || !b->flags || !b->terminal_obs || !b->terminal_state || !b->t_table)
+    if ((!b->reward && !b->reward_f32) || !b->done || !b->flags || !b->terminal_obs || !b->terminal_state || !b->t_table)
         return fail(R6_EINVAL, "a required output buffer is null%s");
     if (p->n_t < 1) return fail(R6_EINVAL, "t_table is empty%s");
     return R6_OK;

@@ -60,7 +60,7 @@ class R6Params(C.Structure):
         ("clip_reward", C.c_int32),
         ("auto_reset", C.c_int32),
         ("n_t", C.c_int32),
-        ("reserved", C.c_int32),
+        ("obs_rows", C.c_int32),
     ]
 
 
@@ -96,7 +96,7 @@ class EnvParams:
         return REWARD_TERMS_VEL if self.shaping_type == "velocity" else REWARD_TERMS_ACC
 
     def to_struct(self, auto_reset: bool = True, clip_reward: bool | None = None,
-                  time_limit: bool = True) -> R6Params:
+                  time_limit: bool = True, obs_rows: int = 0) -> R6Params:
         p = R6Params()
         rc = self.reward_coeff
         p.dt = float(self.timestep)
@@ -125,6 +125,7 @@ class EnvParams:
         p.clip_reward = int(self.clip_reward if clip_reward is None else clip_reward)
         p.auto_reset = int(auto_reset)
         p.n_t = int(len(self.t_table))
+        p.obs_rows = int(obs_rows)
         return p
 
 

@@ -9,7 +9,10 @@ Drop-in for what SB3 builds around the reference's `make_env()` (main_6DOF.py:44
 
 Two call levels:
   * `step_host(actions)` / `reset_host()`: pinned-host-buffer fast path (no Python per-env work);
-    this is what scales to 2^20 envs and what bench.py's e2e number measures;
+    this is what scales to 2^20 envs and what bench.py's e2e number measures.  With `zero_copy=True`
+    (default) the step kernel reads the actions from, and writes obs / reward / done / flags to,
+    pinned device-mapped host memory directly, so the PCIe traffic overlaps the computation instead
+    of being three serial copies around it;
   * `reset()`, `step_async()`, `step_wait()`, `step()`, ...: the SB3 VecEnv protocol on top of it
     (info dicts are materialised only for envs that finished).
 If stable-baselines3 is importable the class is registered as a virtual subclass of its VecEnv.
@@ -19,9 +22,12 @@ from __future__ import annotations
 import time
 from typing import Any, List, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 import torch
 
+from . import _lib
 from .batch import F_EVENT, F_OOB, F_TRUNCATED, F_LANDING_ALL, FLAG_NAMES, Rocket6DOFBatch
 from .spaces import make_box
 
@@ -35,7 +41,7 @@ class Rocket6DOFVecEnv:
 
     def __init__(self, num_envs: int, env_config: Optional[dict] = None, sb3_config: Optional[dict] = None, *,
                  device="cuda", seed: Optional[int] = None, remove_mass_from_obs: bool = True,
-                 clip_reward: bool = True, time_limit: bool = True, **batch_kw):
+                 clip_reward: bool = True, time_limit: bool = True, zero_copy: bool = True, **batch_kw):
         self.batch = Rocket6DOFBatch(num_envs, env_config, sb3_config, device=device, seed=seed, auto_reset=True,
                                      clip_reward=clip_reward, time_limit=time_limit, **batch_kw)
         self.num_envs = int(num_envs)
@@ -53,6 +59,19 @@ class Rocket6DOFVecEnv:
         self._flags_h = torch.empty(n, dtype=torch.uint8).pin_memory()
         self._actions = None
         self._t_start = time.time()
+        self.zero_copy = bool(zero_copy)
+        if self.zero_copy:
+            # same device state, but the per-step outputs land in the pinned host buffers (UVA: a pinned
+            # torch tensor's data_ptr() is valid on the device) and only `obs_dim` observation rows are written
+            b = self.batch
+            self._p_host = b.params.to_struct(auto_reset=True, clip_reward=clip_reward, time_limit=time_limit,
+                                              obs_rows=self.obs_dim)
+            hb = type(b._b)()
+            for name, _ in hb._fields_:
+                setattr(hb, name, getattr(b._b, name))
+            hb.obs, hb.reward, hb.reward_f32 = self._obs_h.data_ptr(), 0, self._rew_h.data_ptr()
+            hb.done, hb.flags = self._done_h.data_ptr(), self._flags_h.data_ptr()
+            self._b_host = hb
         self.h2d_bytes_per_step = self._act_h.numel() * 4
         self.d2h_bytes_per_step = self._obs_h.numel() * 4 + self._rew_h.numel() * 4 + 2 * n
 
@@ -70,6 +89,16 @@ class Rocket6DOFVecEnv:
         buffers (valid until the next call): obs [N, obs_dim], rewards [N] f32, dones [N] bool."""
         b = self.batch
         a = torch.as_tensor(actions, dtype=torch.float32).reshape(self.num_envs, 3)
+        if self.zero_copy:
+            if not (a.is_pinned() and a.is_contiguous()):
+                self._act_h.copy_(a)
+                a = self._act_h
+            with torch.cuda.device(b.device):
+                _lib.check(b.lib.r6_step(C.byref(self._p_host), C.byref(self._b_host), self.num_envs, b.env_offset,
+                                         a.data_ptr(), b.seed_value, b._stream()), b.lib)
+            b.steps_done += 1
+            torch.cuda.current_stream(b.device).synchronize()
+            return self._obs_h.numpy().T, self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
         if a.is_pinned():                      # caller already staged the actions in pinned memory
             self._act_d.copy_(a, non_blocking=True)
         else:

@@ -1,0 +1,102 @@
+"""The reference-facing Python layer on the GPU: SB3 VecEnv protocol (auto-reset, info keys), the
+pinned-host fast path with and without zero-copy, and the single-env gym facade."""
+import numpy as np
+import pytest
+
+from parity_utils import env_params, f32_ulp_diff, golden, reward_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _actions(n, k, seed=0):
+    return np.random.default_rng(seed).uniform(-1, 1, (k, n, 3)).astype(np.float32)
+
+
+def test_zero_copy_step_host_equals_staged_copies():
+    """Kernel writing straight into mapped pinned memory == kernel + explicit D2H copies, bit for bit."""
+    import torch
+    from rl_rocket_6dof_b200 import make_vec_env
+    n, k = 4096, 220
+    a = make_vec_env(n, device="cuda:0", seed=5, zero_copy=True)
+    b = make_vec_env(n, device="cuda:0", seed=5, zero_copy=False)
+    oa, ob = a.reset_host().copy(), b.reset_host().copy()
+    assert oa.shape == (n, 13) and oa.dtype == np.float32 and np.array_equal(oa, ob)
+    acts = _actions(n, k)
+    pinned = torch.from_numpy(acts).pin_memory()
+    n_done = 0
+    for j in range(k):
+        ra = a.step_host(pinned[j])              # pinned input: no staging copy at all
+        rb = b.step_host(acts[j])                # numpy input: staged through the pinned buffer
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y), j
+        n_done += int(ra[2].sum())
+    assert n_done > n // 2                       # episodes ended and were auto-reset on both paths
+    assert torch.equal(a.batch.state, b.batch.state) and torch.equal(a.batch.episode_id, b.batch.episode_id)
+    assert a.h2d_bytes_per_step == n * 12 and a.d2h_bytes_per_step == n * (13 * 4 + 4 + 2)
+
+
+def test_vecenv_protocol_and_infos():
+    from rl_rocket_6dof_b200 import make_vec_env
+    from rl_rocket_6dof_b200.vec_env import MonitorTag
+    n, k = 64, 260
+    env = make_vec_env(n, device="cuda:0", seed=9)
+    assert env.num_envs == n and env.observation_space.shape == (13,) and env.action_space.shape == (3,)
+    assert env.env_is_wrapped(MonitorTag) == [True] * n
+    assert env.get_attr("max_thrust", [0, 1]) == [981e3, 981e3]
+    with pytest.raises(AttributeError):
+        env.get_attr("nope")
+    obs = env.reset()
+    assert obs.shape == (n, 13) and obs.dtype == np.float32 and obs.flags["C_CONTIGUOUS"]
+    norm = env.batch.params.state_normalizer
+    ret = np.zeros(n)
+    length = np.zeros(n, np.int64)
+    finished = 0
+    acts = _actions(n, k, seed=3)
+    for j in range(k):
+        env.step_async(acts[j])
+        obs, rews, dones, infos = env.step_wait()
+        assert obs.shape == (n, 13) and rews.dtype == np.float32 and dones.dtype == np.bool_ and len(infos) == n
+        assert np.all(rews >= -1.0) and np.all(rews <= 100.0)          # ClipReward(-1, 100)
+        ret += rews
+        length += 1
+        for i in np.nonzero(dones)[0]:
+            info = infos[i]
+            finished += 1
+            assert set(info) >= {"terminal_observation", "episode", "TimeLimit.truncated", "state_history"}
+            assert info["episode"]["l"] == length[i]
+            assert abs(info["episode"]["r"] - ret[i]) <= 1e-3 * max(1.0, abs(ret[i]))
+            ts = info["state_history"][-1]
+            assert ts.shape == (14,)
+            tob = (ts / norm).astype(np.float32)[:13]
+            assert f32_ulp_diff(info["terminal_observation"], tob).max() <= 1.0
+            assert info["is_done"] != info["TimeLimit.truncated"]
+            assert info["bounds_violation"] or ts[0] <= 1e-2 or info["TimeLimit.truncated"]
+            # the returned obs is already the first observation of the next episode
+            assert not np.array_equal(obs[i], info["terminal_observation"])
+            ret[i] = 0
+            length[i] = 0
+        for i in np.nonzero(~dones)[0][:4]:
+            assert infos[i] == {}
+    assert finished >= n
+    env.close()
+
+
+def test_gym_facade_known_answer():
+    """Rocket6DOF(**env_config) with ICRange = 0 reproduces the RNG-free three-step fixture."""
+    from rl_rocket_6dof_b200 import Rocket6DOF, load_config
+    _, cfg = load_config()
+    cfg = {**cfg, "ICRange": [0] * 14}
+    rec = golden("env_ka")
+    env = Rocket6DOF(**cfg, device="cuda:0")
+    obs0 = env.reset()
+    assert obs0.shape == (14,) and obs0.dtype == np.float32
+    assert np.array_equal(env.get_state(), rec["ic"][0])
+    for k in range(3):
+        obs, reward, done, info = env.step(rec["action"][k])
+        assert f32_ulp_diff(obs, rec["obs"][k]).max() < 0.5
+        assert reward_err(reward, rec["reward"][k]) <= 1e-9
+        assert done == bool(rec["done"][k]) and info["bounds_violation"] == bool(rec["oob"][k])
+        assert len(info["state_history"]) == k + 2 and len(info["rewards_dict"]) == 7
+    assert abs(env.used_mass() - (rec["ic"][0][13] - rec["state"][2][13])) <= 1e-6
+    with pytest.raises(KeyError):
+        Rocket6DOF(IC=cfg["IC"], ICRange=cfg["ICRange"], device="cuda:0")     # no landing_params -> 'waypoint'
