@@ -264,6 +264,25 @@ def run_b200(args):
     ms_roll = max_over_ranks(e0.elapsed_time(e1))
     barrier()
 
+    # ---- optional float32 dynamics path (own error bound, tests/test_gpu_fp32.py): same workload ----
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    env32 = Rocket6DOFBatch(n, device=dev, seed=42, env_offset=rank * n, num_envs_global=world * n, precision="fp32",
+                            record_attempts=True)
+    env32.reset()
+    env32.rollout(args.preroll)
+    for w in range(W):
+        env32.step(acts[w % R])
+    barrier()
+    e0.record(stream)
+    for k in range(K):
+        env32.step(acts[k % R])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_f32 = max_over_ranks(e0.elapsed_time(e1))
+    mean_att32 = float(env32.nattempts.to(torch.float64).mean())
+    barrier()
+    del env32
+
     # ---- fixed-policy closed loop: SB3 MlpPolicy actor fused into the rollout kernel ----------
     from rl_rocket_6dof_b200 import policy as _policy
     from rl_rocket_6dof_b200.batch import ACT_MLP
@@ -348,6 +367,13 @@ def run_b200(args):
         "peaks_measured": {"fp64_tflops": peaks["fp64"], "fp32_tflops": peaks["fp32"]},
         "rollout_fused": {"value": world * n * K / (ms_roll * 1e-3), "unit": UNIT, "ms_per_step": ms_roll / K,
                           "launches": 1, "actions": "in-kernel Philox4x32-10"},
+        "fp32_path": {"value": world * n * K / (ms_f32 * 1e-3), "unit": UNIT, "ms_per_step": ms_f32 / K, "dtype": "f32",
+                      "mean_rk_attempts": mean_att32,
+                      "roofline": {"bound": "fp32", "achieved": n / (ms_f32 / K * 1e-3) * (F_FIX + F_ATT * mean_att32) / 1e12,
+                                   "peak": peaks["fp32"], "unit": "TFLOP/s",
+                                   "frac": n / (ms_f32 / K * 1e-3) * (F_FIX + F_ATT * mean_att32) / 1e12 / peaks["fp32"]},
+                      "bytes_per_env_step": 208.0,
+                      "note": "R6_PREC_F32: float32 state + integrator, float64 reward/flags; bound stated in tests/test_gpu_fp32.py"},
         "rollout_policy": {"value": world * n * KP / (ms_pol * 1e-3), "unit": UNIT, "ms_per_step": ms_pol / KP,
                            "launches": 1, "actions": "fused MlpPolicy 13-128-64-3 tanh, fp32, deterministic",
                            "weights": wsrc},

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 5
+#define R6_ABI_VERSION 6
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -58,6 +58,12 @@ enum {
     R6_S_EPISODES = 0, R6_S_RETURN_SUM, R6_S_LENGTH_SUM, R6_S_LANDED,
     R6_S_GROUND, R6_S_OOB, R6_S_TRUNCATED, R6_S_STEPS
 };
+
+/* R6Params.precision: arithmetic and storage type of the dynamics */
+#define R6_PREC_F64 0  /* parity path: state / terminal_state are float64 [14][n]; <= 1e-9 vs the reference */
+#define R6_PREC_F32 1  /* throughput path: state / terminal_state are float32 [14][n] (pass the float* through the
+                          double* members); integrator in float32 with its own stated bound, reward / flags
+                          evaluated by the float64 code on the widened state */
 
 /* action sources of r6_rollout */
 #define R6_ACT_PHILOX 0  /* uniform(-1,1) float32 from Philox4x32-10 (synthetic random policy) */
@@ -93,12 +99,14 @@ typedef struct R6Params {
     int32_t n_t;                /* entries in R6Buffers.t_table */
     int32_t obs_rows;           /* rows of obs[] / terminal_obs[] the kernels write: 0 or 14 = all, 13 = RemoveMassFromObs
                                    (saves the mass row when obs[] is mapped host memory) */
+    int32_t precision;          /* R6_PREC_F64 / R6_PREC_F32 */
+    int32_t reserved;
 } R6Params;
 
 /* Device pointers. n = number of local envs. Nullable members are marked. */
 typedef struct R6Buffers {
     /* persistent env state */
-    double *state;          /* [14][n] float64 (Simulator6DOF.state) */
+    double *state;          /* [14][n] float64 (Simulator6DOF.state); float32 [14][n] when precision = R6_PREC_F32 */
     float *m0;              /* [n] initial mass of the episode (simulator.py:42) */
     float *v0;              /* [n] ||IC[3:6]|| (rocket_env.py:651) */
     int32_t *step_count;    /* [n] steps taken in the episode (time = t_table[step_count]) */
@@ -110,7 +118,7 @@ typedef struct R6Buffers {
     uint8_t *done;          /* [n] done OR truncated (what a VecEnv reports) */
     uint8_t *flags;         /* [n] R6_F_* */
     float *terminal_obs;    /* [14][n] obs of the last step of a finished episode ("terminal_observation") */
-    double *terminal_state; /* [14][n] SIM.states[-1] of a finished episode (montecarlo_script.py:35) */
+    double *terminal_state; /* [14][n] SIM.states[-1] of a finished episode (montecarlo_script.py:35); dtype as state */
     double *reward_terms;   /* [7][n] nullable: rewards_dict values in insertion order */
     uint8_t *nattempts;     /* [n] nullable: RK attempts of the step (nfev = 2 + 6*nattempts) */
     int8_t *status;         /* [n] nullable: solve_ivp status of the step (0, 1, -1) */

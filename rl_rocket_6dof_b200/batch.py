@@ -31,7 +31,8 @@ class Rocket6DOFBatch:
                  device: str | torch.device = "cuda", seed: Optional[int] = None, auto_reset: bool = True,
                  clip_reward: bool = True, time_limit: bool = True, env_offset: int = 0,
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
-                 ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None):
+                 ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
+                 precision: str = "fp64"):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -48,11 +49,17 @@ class Rocket6DOFBatch:
         self.num_envs_global = int(num_envs_global if num_envs_global is not None else env_offset + num_envs)
         self.seed_value = int(params.seed if seed is None else seed)
         self.auto_reset = auto_reset
-        self._p = params.to_struct(auto_reset=auto_reset, clip_reward=clip_reward, time_limit=time_limit)
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' (parity path) or 'fp32' (throughput path)")
+        self.precision = precision
+        self._struct_kw = dict(auto_reset=auto_reset, clip_reward=clip_reward, time_limit=time_limit,
+                               precision=1 if precision == "fp32" else 0)
+        self._p = params.to_struct(**self._struct_kw)
         n, dev = self.num_envs, self.device
         f64, f32 = torch.float64, torch.float32
+        sdt = f32 if precision == "fp32" else f64      # dtype of state / terminal_state (R6_PREC_*)
         with torch.cuda.device(dev):
-            self.state = torch.zeros(14, n, dtype=f64, device=dev)
+            self.state = torch.zeros(14, n, dtype=sdt, device=dev)
             self.m0 = torch.zeros(n, dtype=f32, device=dev)
             self.v0 = torch.zeros(n, dtype=f32, device=dev)
             self.step_count = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -64,7 +71,7 @@ class Rocket6DOFBatch:
             self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.terminal_obs = torch.zeros(14, n, dtype=f32, device=dev)
-            self.terminal_state = torch.zeros(14, n, dtype=f64, device=dev)
+            self.terminal_state = torch.zeros(14, n, dtype=sdt, device=dev)
             self.ep_info = torch.zeros(2, n, dtype=f32, device=dev)
             self.stats = torch.zeros(8, dtype=f64, device=dev)
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
@@ -166,7 +173,7 @@ class Rocket6DOFBatch:
         if idx is None:
             idx = torch.arange(self.num_envs, device=self.device)
         idx = torch.as_tensor(idx, device=self.device, dtype=torch.long).reshape(-1)
-        self.state[:, idx] = ic.t().to(torch.float64)
+        self.state[:, idx] = ic.t().to(self.state.dtype)
         self.m0[idx] = ic[:, 13]
         # ||v|| float32 with the sdot rule: f32 products, f64 accumulation, one rounding
         v = ic[:, 3:6]
@@ -174,7 +181,7 @@ class Rocket6DOFBatch:
         self.v0[idx] = acc.to(torch.float32).sqrt()
         self.step_count[idx] = step_count
         self.ep_return[idx] = 0
-        self.obs[:, idx] = (self.state[:, idx] / torch.as_tensor(self.params.state_normalizer, device=self.device)[:, None]).to(torch.float32)
+        self.obs[:, idx] = (self.state[:, idx].to(torch.float64) / torch.as_tensor(self.params.state_normalizer, device=self.device)[:, None]).to(torch.float32)
 
     def get_state(self) -> torch.Tensor:
         return self.state

@@ -110,21 +110,57 @@ R6_HD float sdot3(float a0, float a1, float a2, float b0, float b1, float b2)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Precision of the integrator.  R = double is the parity path (<= 1e-9 against the reference);
+// R = float is the optional throughput path with its own stated bound (tests/test_gpu_fp32.py).
+// Everything from here to the end of integrate() is generic in R; literals are written R(x) so that a
+// float instantiation contains no double arithmetic.
+template <class R> struct Real;
+template <> struct Real<double> {
+    static constexpr double eps = 2.220446049250313e-16;
+    static constexpr double tiny = 1e-300;
+};
+template <> struct Real<float> {
+    static constexpr float eps = 1.1920929e-07f;
+    static constexpr float tiny = 1e-30f;
+};
+#if defined(__CUDA_ARCH__)
+R6_HD float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+R6_HD float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#else
+R6_HD float fast_rcp(float x) { return 1.0f / x; }
+R6_HD float fast_sqrt(float x) { return sqrtf(x); }
+#endif
+R6_HD double r_nextafter_up(double t) { return nextafter(t, (double)INFINITY); }
+R6_HD float r_nextafter_up(float t) { return nextafterf(t, INFINITY); }
+
+// ------------------------------------------------------------------------------------------------
 // Dormand–Prince tableau (scipy rk.py:541-565) and the derived "position" tableaus.
-struct Tab {
-    double A[6][5], B[6], C[6], E[7];
-    double AA[6][5];   // AA[s][j] = sum_k A[s][k] A[k][j]   : x_s = x + h C_s v + h^2 sum_j AA[s][j] dv_j
-    double BA[6];      // BA[j]    = sum_k B[k] A[k][j]      : r_new = r + h v + h^2 sum_j BA[j] dv_j
-    double EA[6];      // EA[j]    = sum_k E[k] A[k][j] + E[6] B[j] : e_r = h^2 sum_j EA[j] dv_j
+template <class R>
+struct TabT {
+    R A[6][5], B[6], C[6], E[7];
+    R AA[6][5];   // AA[s][j] = sum_k A[s][k] A[k][j]   : x_s = x + h C_s v + h^2 sum_j AA[s][j] dv_j
+    R BA[6];      // BA[j]    = sum_k B[k] A[k][j]      : r_new = r + h v + h^2 sum_j BA[j] dv_j
+    R EA[6];      // EA[j]    = sum_k E[k] A[k][j] + E[6] B[j] : e_r = h^2 sum_j EA[j] dv_j
     // stage-input rows used by the rolled integrator: x = y + h * sum_j SA[row][j] K_j, positions
     // r = r + h SC[row] v + h^2 sum_j SAA[row][j] dv_j.  rows 1..5 = (A, AA, C); row 6 = (B, BA, 1) gives
     // y_new (the 7th Dormand-Prince stage is evaluated AT y_new); row 7 = (e_0, 0, 1) gives y + h f0,
     // the probe point of select_initial_step.
-    double SA[8][6], SAA[8][6], SC[8];
-    double P[7][4];
-    double Psum[4];    // Psum[m]  = sum_j P[j][m]
-    double PA[6][4];   // PA[j][m] = sum_k P[k][m] A[k][j] + P[6][m] B[j] : dense output of the position rows
+    R SA[8][6], SAA[8][6], SC[8];
+    R P[7][4];
+    R Psum[4];    // Psum[m]  = sum_j P[j][m]
+    R PA[6][4];   // PA[j][m] = sum_k P[k][m] A[k][j] + P[6][m] B[j] : dense output of the position rows
 };
+using Tab = TabT<double>;
 constexpr Tab make_tab()
 {
     Tab t{};
@@ -190,26 +226,53 @@ constexpr Tab make_tab()
     }
     return t;
 }
+constexpr TabT<float> make_tab_f32()
+{
+    const Tab d = make_tab();
+    TabT<float> t{};
+    for (int s = 0; s < 6; s++) {
+        t.B[s] = (float)d.B[s]; t.C[s] = (float)d.C[s]; t.BA[s] = (float)d.BA[s]; t.EA[s] = (float)d.EA[s];
+        for (int j = 0; j < 5; j++) { t.A[s][j] = (float)d.A[s][j]; t.AA[s][j] = (float)d.AA[s][j]; }
+        for (int m = 0; m < 4; m++) t.PA[s][m] = (float)d.PA[s][m];
+    }
+    for (int j = 0; j < 7; j++) {
+        t.E[j] = (float)d.E[j];
+        for (int m = 0; m < 4; m++) t.P[j][m] = (float)d.P[j][m];
+    }
+    for (int r = 0; r < 8; r++) {
+        t.SC[r] = (float)d.SC[r];
+        for (int j = 0; j < 6; j++) { t.SA[r][j] = (float)d.SA[r][j]; t.SAA[r][j] = (float)d.SAA[r][j]; }
+    }
+    for (int m = 0; m < 4; m++) t.Psum[m] = (float)d.Psum[m];
+    return t;
+}
 constexpr Tab kTabHost = make_tab();
+constexpr TabT<float> kTabHostF = make_tab_f32();
 #if defined(__CUDACC__)
-__constant__ Tab kTabDev = make_tab();   // for the rare, dynamically indexed event path
+__constant__ Tab kTabDev = make_tab();               // dynamically indexed by the rolled stage loop
+__constant__ TabT<float> kTabDevF = make_tab_f32();
 #endif
+template <class R> R6_HD const TabT<R> &tab();
 #if defined(__CUDA_ARCH__)
-#define R6_TAB_DYN ::r6::kTabDev
+template <> R6_HD const TabT<double> &tab<double>() { return kTabDev; }
+template <> R6_HD const TabT<float> &tab<float>() { return kTabDevF; }
 #else
-#define R6_TAB_DYN ::r6::kTabHost
+template <> R6_HD const TabT<double> &tab<double>() { return kTabHost; }
+template <> R6_HD const TabT<float> &tab<float>() { return kTabHostF; }
 #endif
 
 // ------------------------------------------------------------------------------------------------
 // Per-step constants consumed by the RHS
-struct StepConst {
-    double Tb0, Tb1, Tb2;   // thrust in the body frame (simulator.py:167-175)
-    double Ji1;             // 1/J_yy (= 1/J_zz), float32-valued (simulator.py:45-50)
-    double gy;              // w0 * (J0 - J1) * Ji1 : gyroscopic coupling (w0 is constant: dw0 = 0)
-    double dm;              // mass rate (simulator.py:140-141)
+template <class R>
+struct StepConstT {
+    R Tb0, Tb1, Tb2;   // thrust in the body frame (simulator.py:167-175)
+    R Ji1;             // 1/J_yy (= 1/J_zz), float32-valued (simulator.py:45-50)
+    R gy;              // w0 * (J0 - J1) * Ji1 : gyroscopic coupling (w0 is constant: dw0 = 0)
+    R dm;              // mass rate (simulator.py:140-141)
     // air-density expansion around the step's initial height (simulator.py:145-150)
-    double h0, rho0, kd;    // rho(h) = rho0 * (1 - d)^p, d = kd*(h - h0), p = -(1 + g0 M / R / L)
+    R h0, rho0, kd;    // rho(h) = rho0 * (1 - d)^p, d = kd*(h - h0), p = -(1 + g0 M / R / L)
 };
+using StepConst = StepConstT<double>;
 
 // physical constants (simulator.py:39-67)
 constexpr double kG0 = 9.81;
@@ -221,64 +284,73 @@ constexpr double kRhoExp = 1 + 9.81 * 0.0289644 / 8.3144598 / (-0.0065);   // ~ 
 constexpr double kLapseOverT = 0.0065 / 288.15;
 constexpr double kCa = 0.82;
 
-// x^e for x > 0.  Kept out of line: it is called once or twice per RK step from four places and the
-// inlined log/exp pair costs ~150 instructions per site (instruction-cache footprint of the kernel).
+// x^e for x > 0 (one call per env-step: the density at the step's initial height)
 R6_HD_NOINLINE double pow_pos(double x, double e) { return exp(e * log(x)); }
-
-R6_HD double density_exact(double h)
+R6_HD float pow_pos(float x, float e)
 {
-    // 1.225 * (T_b/(T_b + h L_b))^e  ==  1.225 * exp(-e * log(1 - c h)),  c = 0.0065/288.15
-    return 1.225 * exp(-kRhoExp * log(1.0 - kLapseOverT * h));
+#if defined(__CUDA_ARCH__)
+    return exp2f(e * __log2f(x));       // MUFU pair, ~1e-6 relative: inside the float path's own round-off
+#else
+    return expf(e * logf(x));
+#endif
 }
 
-R6_HD void density_setup(StepConst &c, double h0)
+template <class R>
+R6_HD R density_exact(R h)
+{
+    // 1.225 * (T_b/(T_b + h L_b))^e  ==  1.225 * (1 - c h)^(-e),  c = 0.0065/288.15
+    return R(1.225) * pow_pos(R(1.0) - R(kLapseOverT) * h, R(-kRhoExp));
+}
+
+template <class R>
+R6_HD void density_setup(StepConstT<R> &c, R h0)
 {
     c.h0 = h0;
-    double base = 1.0 - kLapseOverT * h0;
-    c.rho0 = 1.225 * pow_pos(base, -kRhoExp);
-    c.kd = kLapseOverT / base;
+    const R base = R(1.0) - R(kLapseOverT) * h0;
+    c.rho0 = R(1.225) * pow_pos(base, R(-kRhoExp));
+    c.kd = R(kLapseOverT) / base;
 }
 
 // kExact = false: binomial series of (1 - d)^p around the step's initial height, d = kd (h - h0),
 // p = -kRhoExp, to d^6; the next term is 2.6e-3 d^7, i.e. < 3e-17 for |d| <= 0.01 (|h - h0| <= 400 m).
 // The launcher picks kExact = true when dt is so large that this cannot be guaranteed (dt > 0.25 s).
-template <bool kExact>
-R6_HD double density(const StepConst &c, double h)
+template <bool kExact, class R>
+R6_HD R density(const StepConstT<R> &c, R h)
 {
     if (kExact) return density_exact(h);
-    const double d = c.kd * (h - c.h0);
+    const R d = c.kd * (h - c.h0);
     constexpr double p = -kRhoExp;
-    constexpr double b1 = -p;
-    constexpr double b2 = p * (p - 1) / 2;
-    constexpr double b3 = -p * (p - 1) * (p - 2) / 6;
-    constexpr double b4 = p * (p - 1) * (p - 2) * (p - 3) / 24;
-    constexpr double b5 = -p * (p - 1) * (p - 2) * (p - 3) * (p - 4) / 120;
-    constexpr double b6 = p * (p - 1) * (p - 2) * (p - 3) * (p - 4) * (p - 5) / 720;
-    double s = fma(b6, d, b5);
-    s = fma(s, d, b4);
-    s = fma(s, d, b3);
+    constexpr R b1 = R(-p);
+    constexpr R b2 = R(p * (p - 1) / 2);
+    constexpr R b3 = R(-p * (p - 1) * (p - 2) / 6);
+    constexpr R b4 = R(p * (p - 1) * (p - 2) * (p - 3) / 24);
+    constexpr R b5 = R(-p * (p - 1) * (p - 2) * (p - 3) * (p - 4) / 120);
+    constexpr R b6 = R(p * (p - 1) * (p - 2) * (p - 3) * (p - 4) * (p - 5) / 720);
+    // float: d^4 and beyond are below the rounding of the sum (|d| <= 0.01)
+    R s = (sizeof(R) == 8) ? fma(fma(fma(b6, d, b5), d, b4), d, b3) : b3;
     s = fma(s, d, b2);
     s = fma(s, d, b1);
-    s = fma(s, d, 1.0);
+    s = fma(s, d, R(1.0));
     return c.rho0 * s;
 }
 constexpr double kMaxDtSeries = 0.25;   // (1000 m/s + 60 m/s^2 dt) dt kd <= 0.01 up to here
 
 // env mode constants from the float32 control / initial mass
-R6_HD void consts_env_mode(StepConst &c, float m0, float u0, float u1, float u2, double w0)
+template <class R>
+R6_HD void consts_env_mode(StepConstT<R> &c, float m0, float u0, float u1, float u2, R w0)
 {
     float J0 = f32_mul(f32_mul(0.5f, m0), (float)kRb2);
     float J1 = f32_mul(f32_mul((float)(1.0 / 12), m0), (float)kLen2);
     float Ji1 = f32_div(1.0f, J1);
-    c.Ji1 = (double)Ji1;
-    c.gy = w0 * ((double)J0 - (double)J1) * c.Ji1;
+    c.Ji1 = (R)Ji1;
+    c.gy = w0 * ((R)J0 - (R)J1) * c.Ji1;
     float cy = np_cosf_small(u0), cz = np_cosf_small(u1);
     float sy = np_sinf_small(u0), sz = np_sinf_small(u1);
-    double T = (double)u2;
-    c.Tb0 = (double)f32_mul(cy, cz) * T;
-    c.Tb1 = (double)f32_mul(sy, cz) * T;
-    c.Tb2 = (double)sz * T;
-    c.dm = (double)f32_div(-u2, (float)(9.81 * 360));
+    R T = (R)u2;
+    c.Tb0 = (R)f32_mul(cy, cz) * T;
+    c.Tb1 = (R)f32_mul(sy, cz) * T;
+    c.Tb2 = (R)sz * T;
+    c.dm = (R)f32_div(-u2, (float)(9.81 * 360));
 }
 // raw Simulator6DOF mode: python-list inputs => everything float64 (test_6DOF_simulator.py)
 R6_HD void consts_raw_mode(StepConst &c, double m0, double u0, double u1, double u2, double w0)
@@ -295,19 +367,24 @@ R6_HD void consts_raw_mode(StepConst &c, double m0, double u0, double u1, double
 
 // ------------------------------------------------------------------------------------------------
 // One stage derivative: dv[3], dq[4], dw1, dw2  (dr = v, dw0 = 0, dm = const are implicit)
-struct Deriv {
-    double dv0, dv1, dv2, dq0, dq1, dq2, dq3, dw1, dw2;
+template <class R>
+struct DerivT {
+    R dv0, dv1, dv2, dq0, dq1, dq2, dq3, dw1, dw2;
 };
+using Deriv = DerivT<double>;
 
 // un-normalised rotation matrix entries of the leading-scalar quaternion (q0,q1,q2,q3); R = M / n2
-struct RotU {
-    double m00, m01, m02, m10, m11, m12, m20, m21, m22, n2;
+template <class R>
+struct RotUT {
+    R m00, m01, m02, m10, m11, m12, m20, m21, m22, n2;
 };
-R6_HD RotU rot_unnormalised(double q0, double q1, double q2, double q3)
+using RotU = RotUT<double>;
+template <class R>
+R6_HD RotUT<R> rot_unnormalised(R q0, R q1, R q2, R q3)
 {
-    RotU r;
-    double x2 = q1 * q1, y2 = q2 * q2, z2 = q3 * q3, w2 = q0 * q0;
-    double xy = q1 * q2, zw = q3 * q0, xz = q1 * q3, yw = q2 * q0, yz = q2 * q3, xw = q1 * q0;
+    RotUT<R> r;
+    R x2 = q1 * q1, y2 = q2 * q2, z2 = q3 * q3, w2 = q0 * q0;
+    R xy = q1 * q2, zw = q3 * q0, xz = q1 * q3, yw = q2 * q0, yz = q2 * q3, xw = q1 * q0;
     r.m00 = x2 - y2 - z2 + w2; r.m01 = 2 * (xy - zw);       r.m02 = 2 * (xz + yw);
     r.m10 = 2 * (xy + zw);     r.m11 = -x2 + y2 - z2 + w2;  r.m12 = 2 * (yz - xw);
     r.m20 = 2 * (xz - yw);     r.m21 = 2 * (yz + xw);       r.m22 = -x2 - y2 + z2 + w2;
@@ -316,71 +393,66 @@ R6_HD RotU rot_unnormalised(double q0, double q1, double q2, double q3)
 }
 
 // simulator.py:106-143 — inputs: height, velocity, quaternion, (w1,w2), mass of the stage state
-template <bool kExact>
-R6_HD Deriv rhs(const StepConst &c, double w0, double h, double v0, double v1, double v2, double q0,
-                double q1, double q2, double q3, double w1, double w2, double m)
+template <bool kExact, class R>
+R6_HD DerivT<R> rhs(const StepConstT<R> &c, R w0, R h, R v0, R v1, R v2, R q0, R q1, R q2, R q3, R w1, R w2, R m)
 {
-    Deriv d;
-    const double rho = density<kExact>(c, h);
-    const RotU R = rot_unnormalised(q0, q1, q2, q3);
-    const double inv = fast_rcp(R.n2 * m);       // 1 / (|q|^2 m)
-    const double inv_n2 = inv * m;
+    DerivT<R> d;
+    const R rho = density<kExact>(c, h);
+    const RotUT<R> M = rot_unnormalised(q0, q1, q2, q3);
+    const R inv = fast_rcp(M.n2 * m);       // 1 / (|q|^2 m)
+    const R inv_n2 = inv * m;
     // body-frame velocity (R^T v) and aerodynamic force (simulator.py:216-219)
-    const double vb0 = R.m00 * v0 + R.m10 * v1 + R.m20 * v2;
-    const double vb1 = R.m01 * v0 + R.m11 * v1 + R.m21 * v2;
-    const double vb2 = R.m02 * v0 + R.m12 * v1 + R.m22 * v2;
-    const double vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-    const double ca = (((-0.5 * rho) * vn) * kSref) * kCa * inv_n2;
-    const double A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
-    const double F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
+    const R vb0 = M.m00 * v0 + M.m10 * v1 + M.m20 * v2;
+    const R vb1 = M.m01 * v0 + M.m11 * v1 + M.m21 * v2;
+    const R vb2 = M.m02 * v0 + M.m12 * v1 + M.m22 * v2;
+    const R vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    const R ca = (((R(-0.5) * rho) * vn) * R(kSref)) * R(kCa) * inv_n2;
+    const R A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
+    const R F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
     // simulator.py:127-130, 156-165
-    d.dv0 = (R.m00 * F0 + R.m01 * F1 + R.m02 * F2) * inv - kG0;
-    d.dv1 = (R.m10 * F0 + R.m11 * F1 + R.m12 * F2) * inv;
-    d.dv2 = (R.m20 * F0 + R.m21 * F1 + R.m22 * F2) * inv;
+    d.dv0 = (M.m00 * F0 + M.m01 * F1 + M.m02 * F2) * inv - R(kG0);
+    d.dv1 = (M.m10 * F0 + M.m11 * F1 + M.m12 * F2) * inv;
+    d.dv2 = (M.m20 * F0 + M.m21 * F1 + M.m22 * F2) * inv;
     // simulator.py:136, 221-229 (un-normalised quaternion)
-    d.dq0 = 0.5 * (-w0 * q1 - w1 * q2 - w2 * q3);
-    d.dq1 = 0.5 * (w0 * q0 + w2 * q2 - w1 * q3);
-    d.dq2 = 0.5 * (w1 * q0 - w2 * q1 + w0 * q3);
-    d.dq3 = 0.5 * (w2 * q0 + w1 * q1 - w0 * q2);
+    d.dq0 = R(0.5) * (-w0 * q1 - w1 * q2 - w2 * q3);
+    d.dq1 = R(0.5) * (w0 * q0 + w2 * q2 - w1 * q3);
+    d.dq2 = R(0.5) * (w1 * q0 - w2 * q1 + w0 * q3);
+    d.dq3 = R(0.5) * (w2 * q0 + w1 * q1 - w0 * q2);
     // simulator.py:137, 232-244: tau = [0, 15 T2 - 5 A2, -15 T1 + 5 A1];  J = diag(J0, J1, J1)
     d.dw1 = c.Ji1 * (15 * c.Tb2 - 5 * A2) - c.gy * w2;
     d.dw2 = c.Ji1 * (-15 * c.Tb1 + 5 * A1) + c.gy * w1;
     return d;
 }
 
-// state vector layout: 0-2 r, 3-5 v, 6-9 q (scalar first), 10-12 w, 13 m
-template <bool kExact>
-R6_HD Deriv rhs_state(const StepConst &c, const double *y)
-{
-    return rhs<kExact>(c, y[10], y[0], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]);
-}
-
 R6_HD double sq(double x) { return x * x; }
+R6_HD float sq(float x) { return x * x; }
 R6_HD bool sgn(double x) { return signbit(x); }
+R6_HD bool sgn(float x) { return signbit(x); }
 
 // ------------------------------------------------------------------------------------------------
 // Stage storage.  The Runge–Kutta stage loop is ROLLED (one copy of the right-hand side in the
 // instruction stream, coefficients read from the constant bank) and the six stage derivatives
 // K_j = (dv, dq, dw1, dw2) live outside the register file: on the device in shared memory,
-// [stage][component][thread] so that a warp touches 32 consecutive doubles (conflict-free), on the
-// host (tests/hostsim) in a local array.  This keeps the kernel near 128-168 registers instead of
-// 255, i.e. 1.5-2x the resident warps, and the hot loop inside the instruction cache.
+// [stage][component][thread] so that a warp touches 32 consecutive values (conflict-free), on the
+// host (tests/hostsim) in a local array.
 constexpr int kNK = 9;   // stored components per stage
-struct KLocal {
-    double k[6][kNK];
-    R6_HD double get(int j, int c) const { return k[j][c]; }
-    R6_HD void set(int j, int c, double v) { k[j][c] = v; }
+template <class R>
+struct KLocalT {
+    R k[6][kNK];
+    R6_HD R get(int j, int c) const { return k[j][c]; }
+    R6_HD void set(int j, int c, R v) { k[j][c] = v; }
 };
+using KLocal = KLocalT<double>;
 #if defined(__CUDACC__)
-template <int kThreadsPerBlock>
+template <class R, int kThreadsPerBlock>
 struct KShared {
-    double *base;   // smem + threadIdx.x
-    __device__ __forceinline__ double get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
-    __device__ __forceinline__ void set(int j, int c, double v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
+    R *base;   // smem + threadIdx.x
+    __device__ __forceinline__ R get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
+    __device__ __forceinline__ void set(int j, int c, R v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
 };
 #endif
-template <class KS>
-R6_HD void k_store(KS &K, int j, const Deriv &d)
+template <class KS, class R>
+R6_HD void k_store(KS &K, int j, const DerivT<R> &d)
 {
     K.set(j, 0, d.dv0); K.set(j, 1, d.dv1); K.set(j, 2, d.dv2);
     K.set(j, 3, d.dq0); K.set(j, 4, d.dq1); K.set(j, 5, d.dq2); K.set(j, 6, d.dq3);
@@ -393,28 +465,28 @@ R6_HD void k_store(KS &K, int j, const Deriv &d)
 // scipy.optimize.brentq does (xtol = rtol = 4 eps, maxiter 100), then y = sol(t_event).
 // Position rows use the PA tableau (their stage derivatives are stage velocities), the mass row is
 // dm * Psum, the w0 row is 0.  Rare (at most once per episode) => not inlined.
-template <class KS>
-R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, out: y(t_event) */, const KS &K,
-                                  const Deriv &fn, double t_old, double t_new)
+template <class KS, class R>
+R6_HD_NOINLINE void event_resolve(const StepConstT<R> &c, R *y /* in: y_old, out: y(t_event) */, const KS &K,
+                                  const DerivT<R> &fn, R t_old, R t_new)
 {
-    const Tab &T = R6_TAB_DYN;
-    const double h = t_new - t_old;
-    double qx[4];   // Q row of the height component
+    const TabT<R> &T = tab<R>();
+    const R h = t_new - t_old;
+    R qx[4];   // Q row of the height component
     for (int m = 0; m < 4; m++) {
-        double a = 0;
+        R a = 0;
         for (int j = 0; j < 6; j++) a += T.PA[j][m] * K.get(j, 0);
         qx[m] = y[3] * T.Psum[m] + h * a;
     }
-    const double x_old = y[0];
-    auto ev = [&](double t) {
-        const double x = (t - t_old) / h;
-        const double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
+    const R x_old = y[0];
+    auto ev = [&](R t) {
+        const R x = (t - t_old) / h;
+        const R p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
         return h * (qx[0] * p0 + qx[1] * p1 + qx[2] * p2 + qx[3] * p3) + x_old;
     };
-    const double eps4 = 4 * 2.220446049250313e-16;
-    double xpre = t_old, xcur = t_new, xblk = 0, fblk = 0, spre = 0, scur = 0;
-    double fpre = ev(xpre), fcur = ev(xcur);
-    double root = xcur;
+    const R eps4 = 4 * Real<R>::eps;
+    R xpre = t_old, xcur = t_new, xblk = 0, fblk = 0, spre = 0, scur = 0;
+    R fpre = ev(xpre), fcur = ev(xcur);
+    R root = xcur;
     if (fpre == 0) root = xpre;
     else if (fcur == 0) root = xcur;
     else if (sgn(fpre) == sgn(fcur)) root = xcur;   // scipy raises; cannot happen after the sign test
@@ -427,18 +499,18 @@ R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, ou
                 xpre = xcur; xcur = xblk; xblk = xpre;
                 fpre = fcur; fcur = fblk; fblk = fpre;
             }
-            const double delta = (eps4 + eps4 * fabs(xcur)) / 2;
-            const double sbis = (xblk - xcur) / 2;
+            const R delta = (eps4 + eps4 * fabs(xcur)) / 2;
+            const R sbis = (xblk - xcur) / 2;
             if (fcur == 0 || fabs(sbis) < delta) break;
             if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
-                double stry;
+                R stry;
                 if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
                 else {
-                    const double dpre = (fpre - fcur) / (xpre - xcur);
-                    const double dblk = (fblk - fcur) / (xblk - xcur);
+                    const R dpre = (fpre - fcur) / (xpre - xcur);
+                    const R dblk = (fblk - fcur) / (xblk - xcur);
                     stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
                 }
-                const double lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
+                const R lim = fmin(fabs(spre), 3 * fabs(sbis) - delta);
                 if (2 * fabs(stry) < lim) { spre = scur; scur = stry; }
                 else { spre = sbis; scur = sbis; }
             } else { spre = sbis; scur = sbis; }
@@ -450,32 +522,32 @@ R6_HD_NOINLINE void event_resolve(const StepConst &c, double *y /* in: y_old, ou
         root = xcur;
     }
     // y = sol(root)
-    const double x = (root - t_old) / h;
-    double p[4];
+    const R x = (root - t_old) / h;
+    R p[4];
     p[0] = x; p[1] = p[0] * x; p[2] = p[1] * x; p[3] = p[2] * x;
-    double pp[7];   // pp[j] = sum_m P[j][m] p_m ; ppa[j] for the position rows ; ps = sum_m Psum[m] p_m
-    double ppa[6], ps = 0;
+    R pp[7];   // pp[j] = sum_m P[j][m] p_m ; ppa[j] for the position rows ; ps = sum_m Psum[m] p_m
+    R ppa[6], ps = 0;
     for (int j = 0; j < 7; j++) {
-        double a = 0;
+        R a = 0;
         for (int m = 0; m < 4; m++) a += T.P[j][m] * p[m];
         pp[j] = a;
     }
     for (int j = 0; j < 6; j++) {
-        double a = 0;
+        R a = 0;
         for (int m = 0; m < 4; m++) a += T.PA[j][m] * p[m];
         ppa[j] = a;
     }
     for (int m = 0; m < 4; m++) ps += T.Psum[m] * p[m];
-    const double fnv[kNK] = {fn.dv0, fn.dv1, fn.dv2, fn.dq0, fn.dq1, fn.dq2, fn.dq3, fn.dw1, fn.dw2};
+    const R fnv[kNK] = {fn.dv0, fn.dv1, fn.dv2, fn.dq0, fn.dq1, fn.dq2, fn.dq3, fn.dw1, fn.dw2};
     // positions first (they need the old velocities)
     for (int i = 0; i < 3; i++) {
-        double a = 0;
+        R a = 0;
         for (int j = 0; j < 6; j++) a += ppa[j] * K.get(j, i);
         y[i] = y[i] + h * (y[3 + i] * ps + h * a);
     }
     const int comp[kNK] = {3, 4, 5, 6, 7, 8, 9, 11, 12};
     for (int cidx = 0; cidx < kNK; cidx++) {
-        double a = pp[6] * fnv[cidx];
+        R a = pp[6] * fnv[cidx];
         for (int j = 0; j < 6; j++) a += pp[j] * K.get(j, cidx);
         y[comp[cidx]] = y[comp[cidx]] + h * a;
     }
@@ -503,6 +575,17 @@ R6_HD double inv_root5(double x)
     return exp(-0.2 * log(x));
 #endif
 }
+R6_HD float inv_root5(float x)
+{
+#if defined(__CUDA_ARCH__)
+    const float xc = fminf(fmaxf(x, 1e-30f), 1e30f);
+    float y = exp2f(-0.2f * __log2f(xc));
+    const float y2 = y * y;
+    return fmaf(0.2f * y, fmaf(-xc, y2 * y2 * y, 1.0f), y);
+#else
+    return expf(-0.2f * logf(x));
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------
 // solve_ivp(fun, [t, t+dt], y, events=height) with all defaults.  y in/out (quaternion NOT yet
@@ -514,74 +597,74 @@ R6_HD double inv_root5(double x)
 // evaluation point is always  y + h * sum_j SA[row][j] K_j  (rows of the extended tableau above), built
 // by one rolled loop.  This keeps the hot instruction footprint to a few KB (the instruction cache is
 // what the unrolled formulation was bound by) at the price of a switch per evaluation.
-template <bool kExact, class KS>
-R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS &K)
+template <bool kExact, class KS, class R>
+R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
 {
-    const Tab &T = R6_TAB_DYN;
-    constexpr double rtol = 1e-3, atol = 1e-6;
-    constexpr double inv_sqrt14 = 0.2672612419124244;   // 1/sqrt(14)
+    const TabT<R> &T = tab<R>();
+    constexpr R rtol = R(1e-3), atol = R(1e-6);
+    constexpr R inv_sqrt14 = R(0.2672612419124244);   // 1/sqrt(14)
     constexpr int kStageF0 = -1, kStageProbe = 0;        // stage >= 1: Dormand-Prince stage index (6 = f(y_new))
-    const double t_bound = t + dt;
-    const double L = fabs(t_bound - t);                  // common.py:100 (interval length as SciPy computes it)
-    const double w0 = y[10];
+    const R t_bound = t + dt;
+    const R L = fabs(t_bound - t);                       // common.py:100 (interval length as SciPy computes it)
+    const R w0 = y[10];
     density_setup(c, y[0]);
     // evaluation point (height, v, q, w1, w2, m) + the two horizontal positions of y_new
-    double xh = y[0], xv0 = y[3], xv1 = y[4], xv2 = y[5], xq0 = y[6], xq1 = y[7], xq2 = y[8], xq3 = y[9];
-    double xw1 = y[11], xw2 = y[12], xm = y[13], xr1 = y[1], xr2 = y[2];
+    R xh = y[0], xv0 = y[3], xv1 = y[4], xv2 = y[5], xq0 = y[6], xq1 = y[7], xq2 = y[8], xq3 = y[9];
+    R xw1 = y[11], xw2 = y[12], xm = y[13], xr1 = y[1], xr2 = y[2];
     int stage = kStageF0;
-    double h = 0, h_abs = 0, t_new = t;
-    double g = y[0];
+    R h = 0, h_abs = 0, t_new = t;
+    R g = y[0];
     int status = -2;
     bool rejected = false;
     natt = 0;
     for (;;) {
-        const Deriv d = rhs<kExact>(c, w0, xh, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2, xm);
+        const DerivT<R> d = rhs<kExact>(c, w0, xh, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2, xm);
         bool begin_attempt = false;
         int row;
-        double hh;
+        R hh;
         if (stage >= 1 && stage <= 5) {
             k_store(K, stage, d);
             stage += 1;
             row = stage; hh = h;
         } else if (stage == 6) {
             // ---- d = f(y_new): error estimate (rk.py:104-109, 141-142), accept / reject (rk.py:144-163) ----
-            double es[kNK], er[3];
+            R es[kNK], er[3];
 #pragma unroll
             for (int i = 0; i < kNK; i++) es[i] = 0;
 #pragma unroll
             for (int i = 0; i < 3; i++) er[i] = 0;
 #pragma unroll 1
             for (int j = 0; j < 6; j++) {
-                const double e = T.E[j], ea = T.EA[j];
+                const R e = T.E[j], ea = T.EA[j];
 #pragma unroll
                 for (int i = 0; i < kNK; i++) {
-                    const double k = K.get(j, i);
+                    const R k = K.get(j, i);
                     es[i] = fma(e, k, es[i]);
                     if (i < 3) er[i] = fma(ea, k, er[i]);
                 }
             }
-            const double e6 = T.E[6];
-            const double fnv[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
-            const double yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
-            const double yw[12] = {xh, xr1, xr2, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2};
-            const double h2 = h * h;
+            const R e6 = T.E[6];
+            const R fnv[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
+            const R yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
+            const R yw[12] = {xh, xr1, xr2, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2};
+            const R h2 = h * h;
             // the w0 and mass rows contribute exactly 0 to the error norm
-            double ssum = 0;
+            R ssum = 0;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                const double sc = fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol);
-                const double e = (i < 3) ? h2 * er[i] : h * fma(e6, fnv[i - 3], es[i - 3]);
+                const R sc = fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol);
+                const R e = (i < 3) ? h2 * er[i] : h * fma(e6, fnv[i - 3], es[i - 3]);
                 ssum += sq(e * fast_rcp(sc));
             }
-            const double err = fast_sqrt(ssum) * inv_sqrt14;
-            const double raw = (err == 0) ? 10.0 : 0.9 * inv_root5(err);        // SAFETY * err^(-1/5)
+            const R err = fast_sqrt(ssum) * inv_sqrt14;
+            const R raw = (err == 0) ? R(10.0) : R(0.9) * inv_root5(err);        // SAFETY * err^(-1/5)
             if (err < 1) {
-                double factor = fmin(10.0, raw);
-                if (rejected) factor = fmin(1.0, factor);
+                R factor = fmin(R(10.0), raw);
+                if (rejected) factor = fmin(R(1.0), factor);
                 h_abs *= factor;
                 // accepted: ivp.py:659-699
-                const double t_old = t;
-                const double g_new = xh;
+                const R t_old = t;
+                const R g_new = xh;
                 const bool ev = (g <= 0 && g_new >= 0) || (g >= 0 && g_new <= 0);
                 t = t_new;
                 if (t - t_bound >= 0) status = 0;
@@ -597,23 +680,23 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS 
                 g = g_new;
                 rejected = false;
             } else {
-                h_abs *= fmax(0.2, raw);
+                h_abs *= fmax(R(0.2), raw);
                 rejected = true;
             }
             begin_attempt = true;
         } else if (stage == kStageF0) {
             // ---- d = f0 (rk.py:96); select_initial_step part 1 (common.py:105-119), order 4 ----
             k_store(K, 0, d);
-            double s0 = 0, s1 = 0;
-            const double fv[14] = {y[3], y[4], y[5], d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, 0.0, d.dw1, d.dw2, c.dm};
+            R s0 = 0, s1 = 0;
+            const R fv[14] = {y[3], y[4], y[5], d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, R(0), d.dw1, d.dw2, c.dm};
 #pragma unroll
             for (int i = 0; i < 14; i++) {
-                const double isc = fast_rcp(fma(fabs(y[i]), rtol, atol));
+                const R isc = fast_rcp(fma(fabs(y[i]), rtol, atol));
                 s0 += sq(y[i] * isc);
                 s1 += sq(fv[i] * isc);
             }
-            const double d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
-            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 * fast_rcp(d1);
+            const R d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
+            R h0 = (d0 < R(1e-5) || d1 < R(1e-5)) ? R(1e-6) : R(0.01) * d0 * fast_rcp(d1);
             h0 = fmin(h0, L);
             h = h0;            // probe step; d1 is parked in h_abs until the probe comes back
             h_abs = d1;
@@ -621,27 +704,28 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS 
             row = 7; hh = h0;
         } else {
             // ---- d = f(y + h0 f0); select_initial_step part 2 (common.py:121-134) ----
-            const double h0 = h, d1 = h_abs;
+            const R h0 = h, d1 = h_abs;
             // (f1 - f0)/scale: position rows are h0*dv, the w0 and mass rows are 0
-            const double f0v[kNK] = {K.get(0, 0), K.get(0, 1), K.get(0, 2), K.get(0, 3), K.get(0, 4), K.get(0, 5),
-                                     K.get(0, 6), K.get(0, 7), K.get(0, 8)};
-            const double f1v[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
-            const double yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
-            double s2 = 0;
+            const R f0v[kNK] = {K.get(0, 0), K.get(0, 1), K.get(0, 2), K.get(0, 3), K.get(0, 4), K.get(0, 5),
+                                K.get(0, 6), K.get(0, 7), K.get(0, 8)};
+            const R f1v[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
+            const R yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
+            R s2 = 0;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                const double isc = fast_rcp(fma(fabs(yo[i]), rtol, atol));
-                const double e = (i < 3) ? h0 * f0v[i] : f1v[i - 3] - f0v[i - 3];
+                const R isc = fast_rcp(fma(fabs(yo[i]), rtol, atol));
+                const R e = (i < 3) ? h0 * f0v[i] : f1v[i - 3] - f0v[i - 3];
                 s2 += sq(e * isc);
             }
-            const double d2 = fast_sqrt(s2) * inv_sqrt14 * fast_rcp(h0);
-            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_root5(100.0 * fmax(d1, d2));
+            const R d2 = fast_sqrt(s2) * inv_sqrt14 * fast_rcp(h0);
+            const R tiny15 = R(1e-15);
+            const R h1 = (d1 <= tiny15 && d2 <= tiny15) ? fmax(R(1e-6), h0 * R(1e-3)) : inv_root5(R(100.0) * fmax(d1, d2));
             h_abs = fmin(fmin(100 * h0, h1), L);
             begin_attempt = true;
         }
         if (begin_attempt) {
             // ---- RungeKutta._step_impl entry (rk.py:111-131) ----
-            const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+            const R min_step = 10 * fabs(r_nextafter_up(t) - t);
             if (h_abs < min_step) {
                 if (rejected) { status = -1; break; }
                 h_abs = min_step;
@@ -656,20 +740,20 @@ R6_HD int integrate(StepConst &c, double *y, double t, double dt, int &natt, KS 
         }
         // ---- evaluation point of the next RHS call: rk_step (rk.py:58-66) with the row's coefficients ----
         {
-            double acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
+            R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
 #pragma unroll
             for (int i = 0; i < kNK; i++) acc[i] = 0;
             const int cnt = row < 6 ? row : (row == 6 ? 6 : 1);
 #pragma unroll 1
             for (int j = 0; j < cnt; j++) {
-                const double a = T.SA[row][j], aa = T.SAA[row][j];
-                const double k0 = K.get(j, 0), k1 = K.get(j, 1), k2 = K.get(j, 2);
+                const R a = T.SA[row][j], aa = T.SAA[row][j];
+                const R k0 = K.get(j, 0), k1 = K.get(j, 1), k2 = K.get(j, 2);
                 acc[0] = fma(a, k0, acc[0]); acc[1] = fma(a, k1, acc[1]); acc[2] = fma(a, k2, acc[2]);
                 ar0 = fma(aa, k0, ar0); ar1 = fma(aa, k1, ar1); ar2 = fma(aa, k2, ar2);
 #pragma unroll
                 for (int i = 3; i < kNK; i++) acc[i] = fma(a, K.get(j, i), acc[i]);
             }
-            const double hc = hh * T.SC[row], hh2 = hh * hh;
+            const R hc = hh * T.SC[row], hh2 = hh * hh;
             xh = fma(hh2, ar0, fma(hc, y[3], y[0]));
             xr1 = fma(hh2, ar1, fma(hc, y[4], y[1]));
             xr2 = fma(hh2, ar2, fma(hc, y[5], y[2]));
@@ -794,12 +878,16 @@ inline AngleTests make_angle_tests(const double viol[3], const double land[3])
 struct Derived {
     AngleTests at;
     double inv_norm[R6_NSTATE];   // RN(1 / normalizer[i]) for the exact 3-instruction division below
+    float inv_norm_f[R6_NSTATE];  // the same in float32 (fp32 path: obs = y * inv_norm_f, 1 ulp)
 };
 inline Derived make_derived(const R6Params &p)
 {
     Derived d;
     d.at = make_angle_tests(p.att_traj_limit, p.land_att_limit);
-    for (int i = 0; i < R6_NSTATE; i++) d.inv_norm[i] = 1.0 / p.normalizer[i];
+    for (int i = 0; i < R6_NSTATE; i++) {
+        d.inv_norm[i] = 1.0 / p.normalizer[i];
+        d.inv_norm_f[i] = (float)d.inv_norm[i];
+    }
     return d;
 }
 // Correctly rounded a / b from r = RN(1/b) (Markstein): q = a r; q' = q + (a - b q) r.
@@ -814,6 +902,7 @@ R6_HD float obs_component(const R6Params &p, const Derived &dv, const double *y,
 {
     return f64_to_f32(div_exact(y[i], p.normalizer[i], dv.inv_norm[i]));
 }
+R6_HD float obs_component(const R6Params &, const Derived &dv, const float *y, int i) { return y[i] * dv.inv_norm_f[i]; }
 
 // Extrinsic zyx Euler angles of the float32-cast quaternion (scipy _rotation_xp.py:365-401,
 // 1052-1111), reduced to what the env needs: the two limit tests.  With a = w-y, b = z-x, c = y+w,
@@ -871,9 +960,11 @@ struct PostOut {
 
 // rocket_env.py:206-231 after the simulator step.  S = post-step state with the quaternion already
 // re-normalised in float64 (simulator.py:97).
-R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConst &c, const double *S, float u2,
+template <class RS>
+R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<RS> &cr, const double *S, float u2,
                      float v0_episode, int status, PostOut &o)
 {
+    struct { double Tb0, Tb1, Tb2; } c = {(double)cr.Tb0, (double)cr.Tb1, (double)cr.Tb2};
     float s[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) s[i] = f64_to_f32(S[i]);                      // :206
@@ -959,9 +1050,10 @@ R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConst &c
     o.flags = fl;
 }
 
-R6_HD void normalize_quat(double *y)    // simulator.py:97, 153-154
+template <class R>
+R6_HD void normalize_quat(R *y)    // simulator.py:97, 153-154
 {
-    const double rn = fast_rcp(fast_sqrt(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]));
+    const R rn = fast_rcp(fast_sqrt(y[6] * y[6] + y[7] * y[7] + y[8] * y[8] + y[9] * y[9]));
     y[6] *= rn; y[7] *= rn; y[8] *= rn; y[9] *= rn;
 }
 
@@ -1107,16 +1199,19 @@ R6_HD void mlp_policy(const float *W, const float *x, float &a0, float &a1, floa
 
 // ------------------------------------------------------------------------------------------------
 // Registers carried by the thread that owns an environment, and the glue of one env step
-struct Env {
-    double y[14];
+template <class R>
+struct EnvT {
+    R y[14];
     float m0, v0;
     int k;             // steps taken in the episode
     uint32_t episode;  // episodes started so far (RNG counter)
     double ep_return;
 };
+using Env = EnvT<double>;
 
 // Rocket6DOF.reset: new initial condition (Philox or replay table), Simulator6DOF re-created.
-R6_HD void env_reset(const R6Params &p, const R6Buffers &b, uint64_t seed, int64_t genv, Env &e)
+template <class R>
+R6_HD void env_reset(const R6Params &p, const R6Buffers &b, uint64_t seed, int64_t genv, EnvT<R> &e)
 {
     float ic[14];
     if (b.ic_table != nullptr && b.ic_table_len > 0) {
@@ -1128,7 +1223,7 @@ R6_HD void env_reset(const R6Params &p, const R6Buffers &b, uint64_t seed, int64
         normalize_ic_quaternion(ic);
     }
 #pragma unroll
-    for (int c = 0; c < 14; c++) e.y[c] = (double)ic[c];
+    for (int c = 0; c < 14; c++) e.y[c] = (R)ic[c];
     e.m0 = ic[13];
     e.v0 = f32_sqrt(sdot3(ic[3], ic[4], ic[5], ic[3], ic[4], ic[5]));
     e.k = 0;
@@ -1145,21 +1240,34 @@ struct StepOut {
     PostOut post;
 };
 
-// One Rocket6DOF.step on the registers of `e` (no reset here).
-template <bool kExact, class KS>
-R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restrict__ t_table, Env &e, float a0,
+// One Rocket6DOF.step on the registers of `e` (no reset here).  R = double: the parity path, integrated
+// on the absolute simulator clock t_table[k] like the reference.  R = float: the dynamics are autonomous, so
+// the step is integrated on the local clock [0, dt] (a float32 absolute time would waste its mantissa
+// on the 150 s range); reward / flags are then evaluated by the same float64 code on the widened state.
+template <bool kExact, class KS, class R>
+R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restrict__ t_table, EnvT<R> &e, float a0,
                     float a1, float a2, StepOut &o, KS &K)
 {
     float u0, u1, u2;
     denormalize_action(p, a0, a1, a2, u0, u1, u2);
-    StepConst c;
+    StepConstT<R> c;
     consts_env_mode(c, e.m0, u0, u1, u2, e.y[10]);
-    const int kk = e.k < p.n_t ? e.k : p.n_t - 1;
-    const double t = t_table[kk];
-    o.status = integrate<kExact>(c, e.y, t, p.dt, o.natt, K);
+    R t = 0;
+    if constexpr (sizeof(R) == 8) {
+        const int kk = e.k < p.n_t ? e.k : p.n_t - 1;
+        t = (R)t_table[kk];
+    }
+    o.status = integrate<kExact>(c, e.y, t, (R)p.dt, o.natt, K);
     normalize_quat(e.y);
     e.k += 1;
-    post_step(p, dv.at, c, e.y, u2, e.v0, o.status, o.post);
+    if constexpr (sizeof(R) == 8) {
+        post_step(p, dv.at, c, reinterpret_cast<const double *>(e.y), u2, e.v0, o.status, o.post);
+    } else {
+        double S[14];
+#pragma unroll
+        for (int i = 0; i < 14; i++) S[i] = (double)e.y[i];
+        post_step(p, dv.at, c, S, u2, e.v0, o.status, o.post);
+    }
     uint32_t fl = o.post.flags;
     const bool done = (fl & (R6_F_EVENT | R6_F_OOB)) != 0;                    // rocket_env.py:213
     const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit

@@ -38,19 +38,26 @@ int check_launch(const char *what)
 #endif
 constexpr int kThreads = R6_THREADS;
 #ifndef R6_MIN_BLOCKS
-#define R6_MIN_BLOCKS 3          /* resident CTAs per SM the register allocation is tuned for */
+#define R6_MIN_BLOCKS 3          /* resident CTAs per SM the register allocation is tuned for (float64 path) */
 #endif
-constexpr int kSmemBytes = 6 * r6::kNK * kThreads * (int)sizeof(double);   // stage storage, 55,296 B per CTA
-constexpr int kSmemMlpBytes = kSmemBytes + r6::kMlpFloats * (int)sizeof(float);   // + packed policy weights (42,000 B)
+#ifndef R6_MIN_BLOCKS_F32
+#define R6_MIN_BLOCKS_F32 4      /* float32 path: half the registers and half the stage storage */
+#endif
+template <class R> constexpr int min_blocks() { return sizeof(R) == 4 ? R6_MIN_BLOCKS_F32 : R6_MIN_BLOCKS; }
+// stage storage per CTA: 55,296 B (float64) / 27,648 B (float32); + packed policy weights (42,000 B) for R6_ACT_MLP
+template <class R> constexpr int smem_bytes() { return 6 * r6::kNK * kThreads * (int)sizeof(R); }
+template <class R> constexpr int smem_mlp_bytes() { return smem_bytes<R>() + r6::kMlpFloats * (int)sizeof(float); }
+constexpr int kSmemBytes = smem_bytes<double>();
 
 using namespace r6;
-using KStore = KShared<kThreads>;
+template <class R> using KStore = KShared<R, kThreads>;
 
-__device__ __forceinline__ KStore make_kstore()
+template <class R>
+__device__ __forceinline__ KStore<R> make_kstore()
 {
     extern __shared__ double r6_smem[];
-    KStore K;
-    K.base = r6_smem + threadIdx.x;
+    KStore<R> K;
+    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
     return K;
 }
 
@@ -75,20 +82,25 @@ __device__ __forceinline__ void stats_flush(const StatAcc &s, double *stats)
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void env_load(const R6Buffers &b, int64_t n, int64_t i, Env &e)
+// state / terminal_state are float64 [14][n] for the parity path and float32 [14][n] when p.precision = R6_PREC_F32
+template <class R>
+__device__ __forceinline__ void env_load(const R6Buffers &b, int64_t n, int64_t i, EnvT<R> &e)
 {
+    const R *state = reinterpret_cast<const R *>(b.state);
 #pragma unroll
-    for (int c = 0; c < 14; c++) e.y[c] = b.state[(int64_t)c * n + i];
+    for (int c = 0; c < 14; c++) e.y[c] = state[(int64_t)c * n + i];
     e.m0 = b.m0[i];
     e.v0 = b.v0[i];
     e.k = b.step_count[i];
     e.episode = b.episode_id[i];
     e.ep_return = b.ep_return[i];
 }
-__device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t i, const Env &e)
+template <class R>
+__device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t i, const EnvT<R> &e)
 {
+    R *state = reinterpret_cast<R *>(b.state);
 #pragma unroll
-    for (int c = 0; c < 14; c++) b.state[(int64_t)c * n + i] = e.y[c];
+    for (int c = 0; c < 14; c++) state[(int64_t)c * n + i] = e.y[c];
     b.m0[i] = e.m0;
     b.v0[i] = e.v0;
     b.step_count[i] = e.k;
@@ -96,8 +108,17 @@ __device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t
     b.ep_return[i] = e.ep_return;
 }
 
+template <class R>
+__device__ __forceinline__ void write_terminal_state(const R6Buffers &b, int64_t n, int64_t i, const R *y)
+{
+    R *ts = reinterpret_cast<R *>(b.terminal_state);
+#pragma unroll
+    for (int c = 0; c < 14; c++) ts[(int64_t)c * n + i] = y[c];
+}
+
+template <class R>
 __device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, const R6Params &p, const Derived &dv,
-                                          const double *y)
+                                          const R *y)
 {
     const int rows = p.obs_rows > 0 ? p.obs_rows : 14;
 #pragma unroll
@@ -105,7 +126,8 @@ __device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, cons
         if (c < rows) obs[(int64_t)c * n + i] = obs_component(p, dv, y, c);   // rocket_env.py:503-504
 }
 
-__device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const Env &e)
+template <class R>
+__device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const EnvT<R> &e)
 {
     s.v[R6_S_STEPS] += 1.0;
     if (o.finished) {
@@ -120,6 +142,7 @@ __device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const En
 }
 
 // ---------------------------------------------------------------------------------------------
+template <class R>
 __global__ void __launch_bounds__(kThreads)
 reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, const uint8_t *mask,
              uint64_t seed)
@@ -127,7 +150,7 @@ reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, i
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     if (mask != nullptr && mask[i] == 0) return;
-    Env e;
+    EnvT<R> e;
     e.episode = b.episode_id[i];
     env_reset(p, b, seed, env_offset + i, e);
     env_store(b, n, i, e);
@@ -135,18 +158,18 @@ reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, i
     if (b.done) b.done[i] = 0;          // un-freezes the env for one-episode (auto_reset = 0) rollouts
 }
 
-template <bool kExact>
-__global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
+template <class R, bool kExact>
+__global__ void __launch_bounds__(kThreads, min_blocks<R>())
 step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
             const float *__restrict__ actions, uint64_t seed)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    KStore K = make_kstore();
+    KStore<R> K = make_kstore<R>();
     StatAcc st;
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
     if (i < n) {
-        Env e;
+        EnvT<R> e;
         env_load(b, n, i, e);
         const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
         StepOut o;
@@ -167,8 +190,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
             if (p.auto_reset) {
                 // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
-#pragma unroll
-                for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+                write_terminal_state(b, n, i, e.y);
                 env_reset(p, b, seed, env_offset + i, e);
             }
         }
@@ -182,19 +204,19 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 // p.auto_reset != 0: finished envs restart (VecEnv semantics).  p.auto_reset == 0: an env that finishes
 // is left frozen with done = 1 and its terminal state / observation recorded (evaluate_policy /
 // Monte-Carlo semantics: one episode per env), and is skipped by later launches until r6_reset.
-template <int kMode, bool kExact>
-__global__ void __launch_bounds__(kThreads, kMode == R6_ACT_MLP ? 2 : R6_MIN_BLOCKS)   // MLP: weights take the 3rd CTA's smem
+template <class R, int kMode, bool kExact>
+__global__ void __launch_bounds__(kThreads, kMode == R6_ACT_MLP ? 2 : min_blocks<R>())   // MLP: weights take the 3rd CTA's smem
 rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, int k_steps,
                const float *__restrict__ act_buf, const R6Mlp mlp, uint64_t seed, int64_t step_base, float *traj_obs,
                float *traj_act, float *traj_rew, uint8_t *traj_done)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    KStore K = make_kstore();
+    KStore<R> K = make_kstore<R>();
     const float *W = nullptr;
     if (kMode == R6_ACT_MLP) {
         // pack the policy weights into shared memory once per CTA (transposes W1, pads W0 rows)
         extern __shared__ double r6_smem[];
-        float *Ws = reinterpret_cast<float *>(r6_smem + 6 * kNK * kThreads);
+        float *Ws = reinterpret_cast<float *>(reinterpret_cast<char *>(r6_smem) + smem_bytes<R>());
         for (int idx = threadIdx.x; idx < kMlpFloats; idx += kThreads) Ws[idx] = mlp_pack_element(mlp, idx);
         __syncthreads();
         W = Ws;
@@ -203,7 +225,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
 #pragma unroll
     for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
     if (i < n && (p.auto_reset || b.done[i] == 0)) {
-        Env e;
+        EnvT<R> e;
         env_load(b, n, i, e);
         StepOut o;
         o.reward = 0; o.flags = 0; o.finished = false; o.natt = 0; o.status = 0;
@@ -231,8 +253,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
             stats_add(st, o, e);
             if (o.finished) {
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
-#pragma unroll
-                for (int c = 0; c < 14; c++) b.terminal_state[(int64_t)c * n + i] = e.y[c];
+                write_terminal_state(b, n, i, e.y);
                 if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
                 if (!p.auto_reset) {
                     // frozen: the rest of the trajectory record (if any) is padding
@@ -264,7 +285,7 @@ sim_raw_kernel(double *state, const double *u, const double *m0, const double *t
                int8_t *status, uint8_t *nattempts)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    KStore K = make_kstore();
+    KStore<double> K = make_kstore<double>();
     if (i >= n) return;
     double y[14];
 #pragma unroll
@@ -313,21 +334,27 @@ int enable_smem(F kernel, int bytes = kSmemBytes)
     if (e != cudaSuccess) return fail(R6_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return R6_OK;
 }
+template <class R>
+int enable_all()
+{
+    int rc = 0;
+    rc |= enable_smem(step_kernel<R, false>, smem_bytes<R>());
+    rc |= enable_smem(step_kernel<R, true>, smem_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, false>, smem_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, true>, smem_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, false>, smem_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, true>, smem_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_MLP, false>, smem_mlp_bytes<R>());
+    rc |= enable_smem(rollout_kernel<R, R6_ACT_MLP, true>, smem_mlp_bytes<R>());
+    return rc;
+}
 int ensure_attributes()
 {
     static thread_local int device_done = -1;
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(R6_ECUDA, "cudaGetDevice failed%s");
     if (dev == device_done) return R6_OK;
-    int rc = 0;
-    rc |= enable_smem(step_kernel<false>);
-    rc |= enable_smem(step_kernel<true>);
-    rc |= enable_smem(rollout_kernel<R6_ACT_PHILOX, false>);
-    rc |= enable_smem(rollout_kernel<R6_ACT_PHILOX, true>);
-    rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, false>);
-    rc |= enable_smem(rollout_kernel<R6_ACT_BUFFER, true>);
-    rc |= enable_smem(rollout_kernel<R6_ACT_MLP, false>, kSmemMlpBytes);
-    rc |= enable_smem(rollout_kernel<R6_ACT_MLP, true>, kSmemMlpBytes);
+    int rc = enable_all<double>() | enable_all<float>();
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -341,6 +368,7 @@ int validate(const R6Params *p, const R6Buffers *b, int64_t n)
 {
     if (!p || !b) return fail(R6_EINVAL, "null params/buffers%s");
     if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (p->precision != R6_PREC_F64 && p->precision != R6_PREC_F32) return fail(R6_EINVAL, "bad precision%s");
     if (!b->state || !b->m0 || !b->v0 || !b->step_count || !b->episode_id || !b->ep_return || !b->obs)
         return fail(R6_EINVAL, "a required state buffer is null%s");
     return R6_OK;
@@ -352,6 +380,42 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
     if ((!b->reward && !b->reward_f32) || !b->done || !b->flags || !b->terminal_obs || !b->terminal_state || !b->t_table)
         return fail(R6_EINVAL, "a required output buffer is null%s");
     if (p->n_t < 1) return fail(R6_EINVAL, "t_table is empty%s");
+    return R6_OK;
+}
+
+template <class R>
+void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset,
+                 const float *actions, uint64_t seed, cudaStream_t s)
+{
+    const unsigned g = (unsigned)blocks_for(n);
+    if (p->dt <= kMaxDtSeries) step_kernel<R, false><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
+    else step_kernel<R, true><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
+}
+
+template <class R>
+int launch_rollout(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset, int32_t k,
+                   int32_t mode, const R6Mlp *mlp, const float *act_buf, uint64_t seed, int64_t step_base,
+                   float *traj_obs, float *traj_act, float *traj_rew, uint8_t *traj_done, cudaStream_t s)
+{
+    const unsigned g = (unsigned)blocks_for(n);
+    const bool exact = !(p->dt <= kMaxDtSeries);
+    R6Mlp m{};
+#define R6_LAUNCH_ROLLOUT(MODE, EXACT, BUF, SMEM)                                                                   \
+    rollout_kernel<R, MODE, EXACT><<<g, kThreads, SMEM, s>>>(*p, *b, dv, n, env_offset, k, BUF, m, seed, step_base, \
+                                                             traj_obs, traj_act, traj_rew, traj_done)
+    if (mode == R6_ACT_PHILOX) {
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, true, nullptr, smem_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, false, nullptr, smem_bytes<R>());
+    } else if (mode == R6_ACT_BUFFER) {
+        if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf, smem_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf, smem_bytes<R>());
+    } else if (mode == R6_ACT_MLP) {
+        if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
+            return fail(R6_EINVAL, "policy weights are null%s");
+        m = *mlp;
+        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_MLP, true, nullptr, smem_mlp_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_MLP, false, nullptr, smem_mlp_bytes<R>());
+    } else
+        return fail(R6_EINVAL, "unsupported action mode%s");
+#undef R6_LAUNCH_ROLLOUT
     return R6_OK;
 }
 
@@ -371,7 +435,10 @@ int r6_reset(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offse
     if (rc) return rc;
     if (n == 0) return R6_OK;
     const Derived dv = make_derived(*p);
-    reset_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, dv, n, env_offset, mask, seed);
+    if (p->precision == R6_PREC_F32)
+        reset_kernel<float><<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, dv, n, env_offset, mask, seed);
+    else
+        reset_kernel<double><<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(*p, *b, dv, n, env_offset, mask, seed);
     return check_launch("r6_reset");
 }
 
@@ -384,10 +451,8 @@ int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset
     if (n == 0) return R6_OK;
     if ((rc = ensure_attributes())) return rc;
     const Derived dv = make_derived(*p);
-    const unsigned g = (unsigned)blocks_for(n);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (p->dt <= kMaxDtSeries) step_kernel<false><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, actions, seed);
-    else step_kernel<true><<<g, kThreads, kSmemBytes, s>>>(*p, *b, dv, n, env_offset, actions, seed);
+    if (p->precision == R6_PREC_F32) launch_step<float>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream);
+    else launch_step<double>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream);
     return check_launch("r6_step");
 }
 
@@ -401,26 +466,13 @@ int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_off
     if (n == 0 || k == 0) return R6_OK;
     if ((rc = ensure_attributes())) return rc;
     const Derived dv = make_derived(*p);
-    const unsigned g = (unsigned)blocks_for(n);
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool exact = !(p->dt <= kMaxDtSeries);
-    R6Mlp m{};
-#define R6_LAUNCH_ROLLOUT(MODE, EXACT, BUF, SMEM)                                                                \
-    rollout_kernel<MODE, EXACT><<<g, kThreads, SMEM, s>>>(*p, *b, dv, n, env_offset, k, BUF, m, seed, step_base, \
-                                                          traj_obs, traj_act, traj_rew, traj_done)
-    if (mode == R6_ACT_PHILOX) {
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, true, nullptr, kSmemBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_PHILOX, false, nullptr, kSmemBytes);
-    } else if (mode == R6_ACT_BUFFER) {
-        if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf, kSmemBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf, kSmemBytes);
-    } else if (mode == R6_ACT_MLP) {
-        if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
-            return fail(R6_EINVAL, "policy weights are null%s");
-        m = *mlp;
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_MLP, true, nullptr, kSmemMlpBytes); else R6_LAUNCH_ROLLOUT(R6_ACT_MLP, false, nullptr, kSmemMlpBytes);
-    } else
-        return fail(R6_EINVAL, "unsupported action mode%s");
-#undef R6_LAUNCH_ROLLOUT
+    if (p->precision == R6_PREC_F32)
+        rc = launch_rollout<float>(p, b, dv, n, env_offset, k, mode, mlp, act_buf, seed, step_base, traj_obs, traj_act,
+                                   traj_rew, traj_done, (cudaStream_t)stream);
+    else
+        rc = launch_rollout<double>(p, b, dv, n, env_offset, k, mode, mlp, act_buf, seed, step_base, traj_obs, traj_act,
+                                    traj_rew, traj_done, (cudaStream_t)stream);
+    if (rc) return rc;
     return check_launch("r6_rollout");
 }
 

@@ -61,6 +61,8 @@ class R6Params(C.Structure):
         ("auto_reset", C.c_int32),
         ("n_t", C.c_int32),
         ("obs_rows", C.c_int32),
+        ("precision", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -96,7 +98,7 @@ class EnvParams:
         return REWARD_TERMS_VEL if self.shaping_type == "velocity" else REWARD_TERMS_ACC
 
     def to_struct(self, auto_reset: bool = True, clip_reward: bool | None = None,
-                  time_limit: bool = True, obs_rows: int = 0) -> R6Params:
+                  time_limit: bool = True, obs_rows: int = 0, precision: int = 0) -> R6Params:
         p = R6Params()
         rc = self.reward_coeff
         p.dt = float(self.timestep)
@@ -126,6 +128,7 @@ class EnvParams:
         p.auto_reset = int(auto_reset)
         p.n_t = int(len(self.t_table))
         p.obs_rows = int(obs_rows)
+        p.precision = int(precision)
         return p
 
 

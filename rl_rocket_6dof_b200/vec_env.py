@@ -64,8 +64,7 @@ class Rocket6DOFVecEnv:
             # same device state, but the per-step outputs land in the pinned host buffers (UVA: a pinned
             # torch tensor's data_ptr() is valid on the device) and only `obs_dim` observation rows are written
             b = self.batch
-            self._p_host = b.params.to_struct(auto_reset=True, clip_reward=clip_reward, time_limit=time_limit,
-                                              obs_rows=self.obs_dim)
+            self._p_host = b.params.to_struct(**{**b._struct_kw, "obs_rows": self.obs_dim})
             hb = type(b._b)()
             for name, _ in hb._fields_:
                 setattr(hb, name, getattr(b._b, name))
