@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 6
+#define R6_ABI_VERSION 7
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -64,6 +64,12 @@ enum {
 #define R6_PREC_F32 1  /* throughput path: state / terminal_state are float32 [14][n] (pass the float* through the
                           double* members); integrator in float32 with its own stated bound, reward / flags
                           evaluated by the float64 code on the widened state */
+
+/* R6Params.reward_mode bits: the optional reward wrappers of my_environment/wrappers/wrappers.py */
+#define R6_RW_ANNEALED 1  /* RewardAnnealing (:39-61; make_annealed_env, main_6DOF.py:55-69): reward = attitude_constraint +
+                             goal_conditions + final_position + final_velocity - xi*(a[2]+1); no out-of-bounds penalty */
+#define R6_RW_VERTICAL 2  /* VerticalAttitudeReward (:128-155): at touchdown with a positive final_velocity term add
+                             clip(2*deg(acos(q0))*weight, -10, 10) */
 
 /* action sources of r6_rollout */
 #define R6_ACT_PHILOX 0  /* uniform(-1,1) float32 from Philox4x32-10 (synthetic random policy) */
@@ -100,6 +106,10 @@ typedef struct R6Params {
     int32_t obs_rows;           /* rows of obs[] / terminal_obs[] the kernels write: 0 or 14 = all, 13 = RemoveMassFromObs
                                    (saves the mass row when obs[] is mapped host memory) */
     int32_t precision;          /* R6_PREC_F64 / R6_PREC_F32 */
+    int32_t reward_mode;        /* R6_RW_* bits, 0 = the plain env reward */
+    double va_threshold;        /* VerticalAttitudeReward threshold_height (1e-3) */
+    double va_weight;           /* VerticalAttitudeReward weight (-0.5) */
+    float xi;                   /* RewardAnnealing thrust penalty (reward_coeff["xi"], default 0.01) */
     int32_t reserved;
 } R6Params;
 

@@ -20,6 +20,9 @@ Fixtures written (all small, committed):
   config2.npz        64 envs x 200 steps full trace  +  512 envs x 200 steps reward/done trace.
   policy_cl.npz      closed-loop best_model_2bo71j9m (numpy MLP), 30 episodes, + the MLP weights.
   velocity.npz       reward_shaping_type='velocity', 1 env x 400 steps.
+  wrappers.npz       reward streams of the optional reward wrappers (wrappers.py:39-61, 128-155) replayed on
+                     the first episodes of policy_cl: RewardAnnealing (make_annealed_env, main_6DOF.py:55-69)
+                     and VerticalAttitudeReward on top of the plain and of the annealed env.
 """
 import argparse
 import copy
@@ -323,6 +326,42 @@ def main():
         out = {k: (v[:T] if isinstance(v, np.ndarray) and v.shape[:1] == (9000,) else v) for k, v in rec.items()}
         out["ic"] = rec["ic"][:n_ep]; out["ic_step"] = rec["ic_step"][:n_ep]
         save("policy_cl", **out, **{"mlp_" + k: v for k, v in p.items()})
+
+    # ---------------------------------------------------------------- wrappers
+    if want("wrappers"):
+        load_reference()
+        from my_environment.wrappers.wrappers import RemoveMassFromObs, RewardAnnealing, VerticalAttitudeReward
+        Rocket6DOF = load_reference()[0]
+        g = np.load(os.path.join(args.out, "policy_cl.npz"))
+        n_ep = 12
+        T = int(g["ic_step"][n_ep])
+        acts = g["action"][:T]
+
+        def run(chain):
+            kw = copy.deepcopy(env_cfg)
+            kw["seed"] = 7                       # the seed policy_cl was recorded with: same ICs, same trajectories
+            base = Rocket6DOF(**kw)
+            env = chain(RemoveMassFromObs(base))
+            rew = np.zeros(T)
+            vert = np.zeros(T)
+            thrust_pen = np.zeros(T)
+            env.reset()
+            for k in range(T):
+                _, r, done, info = env.step(acts[k])
+                rew[k] = r
+                vert[k] = info["rewards_dict"].get("vertical_attitude_reward", 0)
+                thrust_pen[k] = info["rewards_dict"]["thrust_penalty"]
+                assert np.array_equal(base.state, g["state"][k]) and done == bool(g["done"][k])
+                if done:
+                    env.reset()
+            return rew, vert, thrust_pen
+        r_ann, _, tp_ann = run(lambda e: RewardAnnealing(e))
+        r_va, v_a, _ = run(lambda e: VerticalAttitudeReward(RewardAnnealing(e)))
+        r_vb, v_b, _ = run(lambda e: VerticalAttitudeReward(e))
+        assert (v_b != 0).sum() > 0, "fixture does not exercise the vertical-attitude term"
+        save("wrappers", n_steps=T, reward_annealed=r_ann, thrust_penalty_annealed=tp_ann,
+             reward_vertical_annealed=r_va, vertical_term_annealed=v_a,
+             reward_vertical_base=r_vb, vertical_term_base=v_b, xi=env_cfg["reward_coeff"].get("xi", 0.01), threshold_height=1e-3, weight=-0.5)
 
     # ---------------------------------------------------------------- velocity
     if want("velocity"):

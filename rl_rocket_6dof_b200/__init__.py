@@ -12,7 +12,7 @@ GPU raises — there is no CPU path):
 from .params import EnvParams, derive_params, load_config  # noqa: F401
 
 __all__ = ["EnvParams", "derive_params", "load_config", "Rocket6DOFBatch", "Rocket6DOFVecEnv", "Rocket6DOF",
-           "make_env", "make_vec_env"]
+           "make_env", "make_vec_env", "make_annealed_env", "make_annealed_vec_env"]
 
 
 def __getattr__(name):  # lazy: params are usable without torch / CUDA
@@ -25,7 +25,7 @@ def __getattr__(name):  # lazy: params are usable without torch / CUDA
     if name == "Rocket6DOF":
         from .gym_env import Rocket6DOF
         return Rocket6DOF
-    if name in ("make_env", "make_vec_env"):
+    if name in ("make_env", "make_vec_env", "make_annealed_env", "make_annealed_vec_env"):
         from . import factory
         return getattr(factory, name)
     raise AttributeError(name)

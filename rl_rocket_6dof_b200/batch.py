@@ -32,7 +32,7 @@ class Rocket6DOFBatch:
                  clip_reward: bool = True, time_limit: bool = True, env_offset: int = 0,
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
                  ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
-                 precision: str = "fp64"):
+                 precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -53,7 +53,8 @@ class Rocket6DOFBatch:
             raise ValueError("precision must be 'fp64' (parity path) or 'fp32' (throughput path)")
         self.precision = precision
         self._struct_kw = dict(auto_reset=auto_reset, clip_reward=clip_reward, time_limit=time_limit,
-                               precision=1 if precision == "fp32" else 0)
+                               precision=1 if precision == "fp32" else 0, reward_annealing=reward_annealing,
+                               vertical_attitude_reward=vertical_attitude_reward)
         self._p = params.to_struct(**self._struct_kw)
         n, dev = self.num_envs, self.device
         f64, f32 = torch.float64, torch.float32

@@ -1273,6 +1273,22 @@ R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restri
     const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit
     if (trunc) fl |= R6_F_TRUNCATED;
     double r = o.post.reward;
+    if (p.reward_mode & R6_RW_ANNEALED) {
+        // RewardAnnealing.step (wrappers.py:44-61): the env reward is discarded and rebuilt from four
+        // terms of rewards_dict plus -xi*(action[2]+1) (float32: python float times np.float32)
+        const float tp = f32_mul(-p.xi, f32_add(a2, 1.0f));
+        double s = 0;
+        s += o.post.terms[3]; s += o.post.terms[4]; s += o.post.terms[5]; s += o.post.terms[6]; s += (double)tp;
+        r = s;
+        o.post.terms[0] = 0; o.post.terms[1] = (double)tp; o.post.terms[2] = 0;
+    }
+    if (p.reward_mode & R6_RW_VERTICAL) {
+        // VerticalAttitudeReward.step (wrappers.py:134-155) on the float64 post-step state
+        if ((double)e.y[0] < p.va_threshold && o.post.terms[6] > 0) {
+            const double deg = acos((double)e.y[6]) * (180.0 / 3.14159265358979323846);
+            r += fmin(fmax(2 * deg * p.va_weight, -10.0), 10.0);
+        }
+    }
     if (p.clip_reward) r = fmin(fmax(r, p.clip_lo), p.clip_hi);               // main_6DOF.py:40-42
     o.reward = r;
     o.flags = fl;

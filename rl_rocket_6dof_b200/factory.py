@@ -16,3 +16,13 @@ def make_vec_env(num_envs: int, config_path: Optional[str] = None, **kw):
 def make_env(config_path: Optional[str] = None, **kw):
     """The reference's single wrapped env == a 1-env VecEnv (SB3 wraps single envs the same way)."""
     return make_vec_env(1, config_path, **kw)
+
+
+def make_annealed_vec_env(num_envs: int, config_path: Optional[str] = None, **kw):
+    """`make_annealed_env()` of main_6DOF.py:55-69, batched: Monitor(TimeLimit(RewardAnnealing(RemoveMassFromObs(env))))
+    — no ClipReward, reward rebuilt by RewardAnnealing (wrappers.py:39-61)."""
+    return make_vec_env(num_envs, config_path, clip_reward=False, reward_annealing=True, **kw)
+
+
+def make_annealed_env(config_path: Optional[str] = None, **kw):
+    return make_annealed_vec_env(1, config_path, **kw)

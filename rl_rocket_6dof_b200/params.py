@@ -62,6 +62,10 @@ class R6Params(C.Structure):
         ("n_t", C.c_int32),
         ("obs_rows", C.c_int32),
         ("precision", C.c_int32),
+        ("reward_mode", C.c_int32),
+        ("va_threshold", C.c_double),
+        ("va_weight", C.c_double),
+        ("xi", C.c_float),
         ("reserved", C.c_int32),
     ]
 
@@ -98,7 +102,10 @@ class EnvParams:
         return REWARD_TERMS_VEL if self.shaping_type == "velocity" else REWARD_TERMS_ACC
 
     def to_struct(self, auto_reset: bool = True, clip_reward: bool | None = None,
-                  time_limit: bool = True, obs_rows: int = 0, precision: int = 0) -> R6Params:
+                  time_limit: bool = True, obs_rows: int = 0, precision: int = 0, reward_annealing: bool = False,
+                  vertical_attitude_reward=None) -> R6Params:
+        """reward_annealing: RewardAnnealing wrapper (xi = reward_coeff.get("xi", 0.01), wrappers.py:42);
+        vertical_attitude_reward: None or (threshold_height, weight) of VerticalAttitudeReward (wrappers.py:129)."""
         p = R6Params()
         rc = self.reward_coeff
         p.dt = float(self.timestep)
@@ -129,6 +136,10 @@ class EnvParams:
         p.n_t = int(len(self.t_table))
         p.obs_rows = int(obs_rows)
         p.precision = int(precision)
+        p.reward_mode = (1 if reward_annealing else 0) | (2 if vertical_attitude_reward is not None else 0)
+        p.xi = np.float32(rc.get("xi", 0.01))
+        th, wt = vertical_attitude_reward if vertical_attitude_reward is not None else (1e-3, -0.5)
+        p.va_threshold, p.va_weight = float(th), float(wt)
         return p
 
 
