@@ -53,6 +53,14 @@ R6_HD double fast_rcp(double x)
     r = fma(r, e, r);
     return r;
 }
+// one Newton step only (~1e-12 relative): for the tolerance-scaled norms of the step-size controller,
+// where 1e-12 in a scale moves the next step size by 1e-12 and the solution by < 1e-15
+R6_HD double fast_rcp1(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
 R6_HD double fast_sqrt(double x)
 {
     double r;
@@ -77,6 +85,7 @@ R6_HD float f32_sqrt(float a) { return sqrtf(a); }
 R6_HD float f32_fma(float a, float b, float c) { return fmaf(a, b, c); }
 R6_HD float f64_to_f32(double a) { return (float)a; }
 R6_HD double fast_rcp(double x) { return 1.0 / x; }
+R6_HD double fast_rcp1(double x) { return 1.0 / x; }
 R6_HD double fast_sqrt(double x) { return sqrt(x); }
 #endif
 
@@ -140,6 +149,7 @@ R6_HD float fast_sqrt(float x)
 R6_HD float fast_rcp(float x) { return 1.0f / x; }
 R6_HD float fast_sqrt(float x) { return sqrtf(x); }
 #endif
+R6_HD float fast_rcp1(float x) { return fast_rcp(x); }
 R6_HD double r_nextafter_up(double t) { return nextafter(t, (double)INFINITY); }
 R6_HD float r_nextafter_up(float t) { return nextafterf(t, INFINITY); }
 
@@ -302,13 +312,36 @@ R6_HD R density_exact(R h)
     return R(1.225) * pow_pos(R(1.0) - R(kLapseOverT) * h, R(-kRhoExp));
 }
 
+struct RhoSeries { double c[14]; };
+constexpr RhoSeries make_rho_series(double p)
+{
+    RhoSeries r{};
+    r.c[0] = 1.0;
+    for (int k = 0; k < 13; k++) r.c[k + 1] = r.c[k] * (-(p - k)) / (k + 1);
+    return r;
+}
+// Density at the step's initial height: rho0 = 1.225 (1 - x)^p, x = c h0, p = 4.2576.  Because p is close to
+// an integer the binomial coefficients collapse after k = 5 (|b_13| = 3e-5), so for |x| <= 0.08 (|h0| <= 3.5 km,
+// any state inside the reference's bounds box) 13 Horner steps are exact to < 2e-19 and replace a log/exp pair
+// (~200 executed, ~500 static instructions).  Outside that range the out-of-line pow is used.
 template <class R>
 R6_HD void density_setup(StepConstT<R> &c, R h0)
 {
     c.h0 = h0;
-    const R base = R(1.0) - R(kLapseOverT) * h0;
-    c.rho0 = R(1.225) * pow_pos(base, R(-kRhoExp));
-    c.kd = R(kLapseOverT) / base;
+    const R x = R(kLapseOverT) * h0;
+    const R base = R(1.0) - x;
+    c.kd = R(kLapseOverT) * fast_rcp(base);
+    constexpr double p = -kRhoExp;
+    constexpr int kTerms = sizeof(R) == 8 ? 13 : 6;
+    if (fabs(x) <= R(0.08)) {
+        constexpr RhoSeries b = make_rho_series(p);      // b_k = binom(p, k) (-1)^k, at compile time
+        R s = R(b.c[kTerms - 1]);
+#pragma unroll
+        for (int k = kTerms - 2; k >= 0; k--) s = fma(s, x, R(b.c[k]));
+        c.rho0 = R(1.225) * s;
+    } else {
+        c.rho0 = R(1.225) * pow_pos(base, R(-kRhoExp));
+    }
 }
 
 // kExact = false: binomial series of (1 - d)^p around the step's initial height, d = kd (h - h0),
@@ -654,7 +687,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
             for (int i = 0; i < 12; i++) {
                 const R sc = fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol);
                 const R e = (i < 3) ? h2 * er[i] : h * fma(e6, fnv[i - 3], es[i - 3]);
-                ssum += sq(e * fast_rcp(sc));
+                ssum += sq(e * fast_rcp1(sc));
             }
             const R err = fast_sqrt(ssum) * inv_sqrt14;
             const R raw = (err == 0) ? R(10.0) : R(0.9) * inv_root5(err);        // SAFETY * err^(-1/5)
@@ -691,7 +724,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
             const R fv[14] = {y[3], y[4], y[5], d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, R(0), d.dw1, d.dw2, c.dm};
 #pragma unroll
             for (int i = 0; i < 14; i++) {
-                const R isc = fast_rcp(fma(fabs(y[i]), rtol, atol));
+                const R isc = fast_rcp1(fma(fabs(y[i]), rtol, atol));
                 s0 += sq(y[i] * isc);
                 s1 += sq(fv[i] * isc);
             }
@@ -713,7 +746,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
             R s2 = 0;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                const R isc = fast_rcp(fma(fabs(yo[i]), rtol, atol));
+                const R isc = fast_rcp1(fma(fabs(yo[i]), rtol, atol));
                 const R e = (i < 3) ? h0 * f0v[i] : f1v[i - 3] - f0v[i - 3];
                 s2 += sq(e * isc);
             }
@@ -826,8 +859,32 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
         if (fhi == 0) return hi;
         return NAN;
     }
-    double x = from_right ? hi : lo;
-    double fx = from_right ? fhi : flo;
+    double hi_s = hi, fhi_s = fhi;
+    if (from_right) {
+        // The far end of the bracket is the Fujiwara bound, from which Newton on a quartic first creeps in
+        // by factors of 3/4.  Walk that stretch in float32 (FP32 pipe, no safeguards needed: the result is
+        // only a PROPOSAL for a tighter upper end, accepted if float64 confirms lo < x < hi and f(x) > 0).
+        const float g0 = (float)c0, g2 = (float)c2, g3 = (float)c3, g4 = (float)c4;
+        const float g0x4 = 4.0f * g0, g2x2 = 2.0f * g2;
+        float xf = (float)hi;
+#pragma unroll 1
+        for (int it = 0; it < 48; it++) {
+            const float x2 = xf * xf;
+            const float f = f32_fma(f32_fma(g0, x2, g2), x2, f32_fma(g3, xf, g4));
+            const float df = f32_fma(f32_fma(g0x4, x2, g2x2), xf, g3);
+            const float xn = xf - f * (float)fast_rcp(df);
+            if (!(xf - xn > 2e-6f * xf)) break;
+            xf = xn;
+        }
+        const double xs = (double)xf * (1.0 + 1e-5);
+        if (xs > lo && xs < hi) {
+            const double fs = quartic_f(c0, c2, c3, c4, xs);
+            if (fs > 0) { hi_s = xs; fhi_s = fs; }
+        }
+    }
+    hi = hi_s;
+    double x = from_right ? hi_s : lo;
+    double fx = from_right ? fhi_s : flo;
     for (int it = 0; it < 100; it++) {
         const double dfx = quartic_df(c0, c2, c3, x);
         double xn = x - fx * fast_rcp(dfx);
@@ -1240,6 +1297,13 @@ struct StepOut {
     PostOut post;
 };
 
+// VerticalAttitudeReward (wrappers.py:143-150): clip(2 deg(acos(q0)) weight, -10, 10).  Touchdown only => out of line.
+R6_HD_NOINLINE double vertical_attitude_term(double q0, double weight)
+{
+    const double deg = acos(q0) * (180.0 / 3.14159265358979323846);
+    return fmin(fmax(2 * deg * weight, -10.0), 10.0);
+}
+
 // One Rocket6DOF.step on the registers of `e` (no reset here).  R = double: the parity path, integrated
 // on the absolute simulator clock t_table[k] like the reference.  R = float: the dynamics are autonomous, so
 // the step is integrated on the local clock [0, dt] (a float32 absolute time would waste its mantissa
@@ -1284,10 +1348,7 @@ R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restri
     }
     if (p.reward_mode & R6_RW_VERTICAL) {
         // VerticalAttitudeReward.step (wrappers.py:134-155) on the float64 post-step state
-        if ((double)e.y[0] < p.va_threshold && o.post.terms[6] > 0) {
-            const double deg = acos((double)e.y[6]) * (180.0 / 3.14159265358979323846);
-            r += fmin(fmax(2 * deg * p.va_weight, -10.0), 10.0);
-        }
+        if ((double)e.y[0] < p.va_threshold && o.post.terms[6] > 0) r += vertical_attitude_term((double)e.y[6], p.va_weight);
     }
     if (p.clip_reward) r = fmin(fmax(r, p.clip_lo), p.clip_hi);               // main_6DOF.py:40-42
     o.reward = r;

@@ -62,23 +62,26 @@ __device__ __forceinline__ KStore<R> make_kstore()
 }
 
 // ---------------------------------------------------------------------------------------------
-// Episode statistics: warp shuffle reduction, lane 0 issues one atomic per non-zero slot.
-// (No block barrier: warps of a CTA finish their adaptive steps at different times.)
-struct StatAcc {
-    double v[R6_NSTATS];
-};
-__device__ __forceinline__ void stats_flush(const StatAcc &s, double *stats)
+// Episode statistics.  Env-steps are counted per lane and summed over the warp with one REDUX
+// (__reduce_add_sync), lane 0 issuing a single atomic per warp; the per-episode slots are added by the
+// lane whose episode just ended (about one lane per warp every four steps), straight to L2 — no
+// shuffle tree, no block barrier (warps of a CTA finish their adaptive steps at different times) and
+// no accumulator registers carried through the step.
+__device__ __forceinline__ void stats_steps(double *stats, int my_steps)
 {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < R6_NSTATS; k++) {
-        double x = s.v[k];
-        if (__any_sync(0xffffffffu, x != 0.0)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0) atomicAdd(&stats[k], x);
-        }
-    }
+    const int tot = __reduce_add_sync(0xffffffffu, my_steps);
+    if ((threadIdx.x & 31) == 0 && tot != 0) atomicAdd(&stats[R6_S_STEPS], (double)tot);
+}
+template <class R>
+__device__ __noinline__ void stats_episode(double *stats, uint32_t flags, double ep_return, int length)
+{
+    atomicAdd(&stats[R6_S_EPISODES], 1.0);
+    atomicAdd(&stats[R6_S_RETURN_SUM], ep_return);
+    atomicAdd(&stats[R6_S_LENGTH_SUM], (double)length);
+    if ((flags & R6_F_LANDING_ALL) == R6_F_LANDING_ALL) atomicAdd(&stats[R6_S_LANDED], 1.0);
+    if (flags & R6_F_EVENT) atomicAdd(&stats[R6_S_GROUND], 1.0);
+    if (flags & R6_F_OOB) atomicAdd(&stats[R6_S_OOB], 1.0);
+    if (flags & R6_F_TRUNCATED) atomicAdd(&stats[R6_S_TRUNCATED], 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -126,21 +129,6 @@ __device__ __forceinline__ void write_obs(float *obs, int64_t n, int64_t i, cons
         if (c < rows) obs[(int64_t)c * n + i] = obs_component(p, dv, y, c);   // rocket_env.py:503-504
 }
 
-template <class R>
-__device__ __forceinline__ void stats_add(StatAcc &s, const StepOut &o, const EnvT<R> &e)
-{
-    s.v[R6_S_STEPS] += 1.0;
-    if (o.finished) {
-        s.v[R6_S_EPISODES] += 1.0;
-        s.v[R6_S_RETURN_SUM] += e.ep_return;
-        s.v[R6_S_LENGTH_SUM] += (double)e.k;
-        if ((o.flags & R6_F_LANDING_ALL) == R6_F_LANDING_ALL) s.v[R6_S_LANDED] += 1.0;
-        if (o.flags & R6_F_EVENT) s.v[R6_S_GROUND] += 1.0;
-        if (o.flags & R6_F_OOB) s.v[R6_S_OOB] += 1.0;
-        if (o.flags & R6_F_TRUNCATED) s.v[R6_S_TRUNCATED] += 1.0;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 template <class R>
 __global__ void __launch_bounds__(kThreads)
@@ -165,9 +153,6 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     KStore<R> K = make_kstore<R>();
-    StatAcc st;
-#pragma unroll
-    for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
     if (i < n) {
         EnvT<R> e;
         env_load(b, n, i, e);
@@ -184,8 +169,8 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 #pragma unroll
             for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
         }
-        stats_add(st, o, e);
         if (o.finished) {
+            if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
             if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
             if (p.auto_reset) {
                 // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
@@ -197,7 +182,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         write_obs(b.obs, n, i, p, dv, e.y);
         env_store(b, n, i, e);
     }
-    if (b.stats) stats_flush(st, b.stats);
+    if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
 }
 
 // k fused steps, state in registers; actions from Philox, a [k][n][3] buffer or the fused policy MLP.
@@ -221,9 +206,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
         __syncthreads();
         W = Ws;
     }
-    StatAcc st;
-#pragma unroll
-    for (int k = 0; k < R6_NSTATS; k++) st.v[k] = 0;
+    int my_steps = 0;
     if (i < n && (p.auto_reset || b.done[i] == 0)) {
         EnvT<R> e;
         env_load(b, n, i, e);
@@ -250,8 +233,9 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
             env_step<kExact>(p, dv, b.t_table, e, a0, a1, a2, o, K);
             if (traj_rew) traj_rew[(int64_t)j * n + i] = (float)o.reward;
             if (traj_done) traj_done[(int64_t)j * n + i] = o.finished ? 1 : 0;
-            stats_add(st, o, e);
+            my_steps++;
             if (o.finished) {
+                if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
                 write_terminal_state(b, n, i, e.y);
                 if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
@@ -275,7 +259,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
         write_obs(b.obs, n, i, p, dv, e.y);
         env_store(b, n, i, e);
     }
-    if (b.stats) stats_flush(st, b.stats);
+    if (b.stats) stats_steps(b.stats, my_steps);
 }
 
 // Simulator6DOF.step, raw (all-float64) mode
