@@ -285,7 +285,7 @@ def run_b200(args):
 
     # ---- fixed-policy closed loop: SB3 MlpPolicy actor fused into the rollout kernel ----------
     from rl_rocket_6dof_b200 import policy as _policy
-    from rl_rocket_6dof_b200.batch import ACT_MLP
+    from rl_rocket_6dof_b200.batch import ACT_MLP, ACT_MLP_TC
     wpath = os.path.join(ROOT, "tests", "golden", "policy_cl.npz")
     if os.path.exists(wpath):
         wts, wsrc = _policy.load_npz(wpath), "best_model_2bo71j9m actor (tests/golden/policy_cl.npz)"
@@ -302,6 +302,14 @@ def run_b200(args):
     e1.record(stream)
     torch.cuda.synchronize()
     ms_pol = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    env.rollout(KP, ACT_MLP_TC, mlp=wdev)
+    barrier()
+    e0.record(stream)
+    env.rollout(KP, ACT_MLP_TC, mlp=wdev)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_pol_tc = max_over_ranks(e0.elapsed_time(e1))
     barrier()
 
     # ---- end to end through the VecEnv fast path (host actions in, host obs/reward/done out) --
@@ -377,6 +385,10 @@ def run_b200(args):
         "rollout_policy": {"value": world * n * KP / (ms_pol * 1e-3), "unit": UNIT, "ms_per_step": ms_pol / KP,
                            "launches": 1, "actions": "fused MlpPolicy 13-128-64-3 tanh, fp32, deterministic",
                            "weights": wsrc},
+        "rollout_policy_tensor_cores": {"value": world * n * KP / (ms_pol_tc * 1e-3), "unit": UNIT,
+                                        "ms_per_step": ms_pol_tc / KP, "launches": 1,
+                                        "actions": "same network as rollout_policy on mma.sync TF32 tiles, 3xTF32 "
+                                                   "compensation, one warp = 32 envs, activations register-chained"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},

@@ -75,6 +75,8 @@ enum {
 #define R6_ACT_PHILOX 0  /* uniform(-1,1) float32 from Philox4x32-10 (synthetic random policy) */
 #define R6_ACT_MLP 1     /* deterministic SB3 MlpPolicy forward, fused (montecarlo_script.py:57-64) */
 #define R6_ACT_BUFFER 2  /* actions read from a [k][n][3] device buffer */
+#define R6_ACT_MLP_TC 3  /* the same network as R6_ACT_MLP on the tensor cores: one warp = 32 envs, register-chained
+                            mma.sync TF32 tiles with 3xTF32 error compensation (|d action| <= 2e-6 vs R6_ACT_MLP) */
 
 /*
  * Derived constants of Rocket6DOF.__init__ (rocket_env.py:71-134, 159-168), the wrappers of
@@ -180,6 +182,7 @@ int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset
  * mode R6_ACT_MLP:    action = clip(actor(obs[0:13]), -1, 1), the deterministic SB3 MlpPolicy forward
  *                     (float32, weights staged in shared memory) — evaluate_policy of
  *                     montecarlo_script.py:57-64 with the policy inside the kernel;
+ * mode R6_ACT_MLP_TC: as R6_ACT_MLP, evaluated warp-collectively on the tensor cores (csrc/r6_mlp_tc.cuh);
  * mode R6_ACT_BUFFER: action = act_buf[j][i][:].
  * p->auto_reset != 0: finished envs restart inside the kernel (VecEnv semantics).
  * p->auto_reset == 0: one episode per env — an env that finishes keeps done = 1, its terminal

@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import R6Buffers, R6Mlp
 from .params import EnvParams, derive_params, load_config
 
-ACT_PHILOX, ACT_MLP, ACT_BUFFER = 0, 1, 2
+ACT_PHILOX, ACT_MLP, ACT_BUFFER, ACT_MLP_TC = 0, 1, 2, 3
 F_EVENT, F_OOB, F_TRUNCATED = 0x01, 0x02, 0x04
 F_LANDING_ALL = 0xF8
 FLAG_NAMES = ["zero_height", "velocity_limit", "landing_radius", "attitude_limit", "omega_limit"]
@@ -155,7 +155,7 @@ class Rocket6DOFBatch:
             actions = actions.contiguous()
             ab = actions.data_ptr()
         m = None
-        if mode == ACT_MLP:
+        if mode in (ACT_MLP, ACT_MLP_TC):
             if mlp is None:
                 raise ValueError("ACT_MLP needs the policy weights")
             m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])

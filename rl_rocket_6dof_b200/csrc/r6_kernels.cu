@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "r6_core.cuh"
+#include "r6_mlp_tc.cuh"
 
 namespace {
 
@@ -47,6 +48,11 @@ template <class R> constexpr int min_blocks() { return sizeof(R) == 4 ? R6_MIN_B
 // stage storage per CTA: 55,296 B (float64) / 27,648 B (float32); + packed policy weights (42,000 B) for R6_ACT_MLP
 template <class R> constexpr int smem_bytes() { return 6 * r6::kNK * kThreads * (int)sizeof(R); }
 template <class R> constexpr int smem_mlp_bytes() { return smem_bytes<R>() + r6::kMlpFloats * (int)sizeof(float); }
+// tensor-core policy: fragment-ordered weights (43,792 B) + one [16][33] float staging tile per warp
+template <class R> constexpr int smem_tc_bytes()
+{
+    return smem_bytes<R>() + r6::kMlpTcFloats * (int)sizeof(float) + (kThreads / 32) * 16 * 33 * (int)sizeof(float);
+}
 constexpr int kSmemBytes = smem_bytes<double>();
 
 using namespace r6;
@@ -262,6 +268,79 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
     if (b.stats) stats_steps(b.stats, my_steps);
 }
 
+// Closed-loop rollout with the policy on the tensor cores (R6_ACT_MLP_TC): same semantics as
+// rollout_kernel<R, R6_ACT_MLP, false>, but the network is evaluated warp-collectively (r6_mlp_tc.cuh), so the
+// step loop is warp-uniform: lanes without a live env keep taking part in the MMAs and skip the dynamics.
+template <class R>
+__global__ void __launch_bounds__(kThreads, 2)
+rollout_tc_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset, int k_steps,
+                  const R6Mlp mlp, uint64_t seed, float *traj_obs, float *traj_act, float *traj_rew, uint8_t *traj_done)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    KStore<R> K = make_kstore<R>();
+    extern __shared__ double r6_smem[];
+    float *Ws = reinterpret_cast<float *>(reinterpret_cast<char *>(r6_smem) + smem_bytes<R>());
+    for (int idx = threadIdx.x; idx < kMlpTcFloats; idx += kThreads) Ws[idx] = mlp_tc_pack_element(mlp, idx);
+    __syncthreads();
+    float *scratch = Ws + kMlpTcFloats + (threadIdx.x >> 5) * (16 * 33);
+    int my_steps = 0;
+    const bool loaded = i < n && (p.auto_reset || b.done[i] == 0);
+    bool live = loaded;
+    EnvT<R> e;
+    if (loaded) env_load(b, n, i, e);
+    else {
+#pragma unroll
+        for (int c = 0; c < 14; c++) e.y[c] = 0;
+        e.m0 = 1; e.v0 = 0; e.k = 0; e.episode = 0; e.ep_return = 0;
+    }
+    StepOut o;
+    o.reward = 0; o.flags = 0; o.finished = false; o.natt = 0; o.status = 0;
+#pragma unroll 1
+    for (int j = 0; j < k_steps; j++) {
+        if (!__any_sync(0xffffffffu, live)) break;
+        float x[kMlpIn], a0, a1, a2;
+#pragma unroll
+        for (int c = 0; c < kMlpIn; c++) x[c] = obs_component(p, dv, e.y, c);
+        mlp_policy_tc(Ws, scratch, x, a0, a1, a2);
+        if (live) {
+            if (traj_obs) {
+#pragma unroll
+                for (int c = 0; c < 13; c++) traj_obs[((int64_t)j * 13 + c) * n + i] = x[c];
+            }
+            if (traj_act) { float *a = traj_act + ((int64_t)j * n + i) * 3; a[0] = a0; a[1] = a1; a[2] = a2; }
+            env_step<false>(p, dv, b.t_table, e, a0, a1, a2, o, K);
+            if (traj_rew) traj_rew[(int64_t)j * n + i] = (float)o.reward;
+            if (traj_done) traj_done[(int64_t)j * n + i] = o.finished ? 1 : 0;
+            my_steps++;
+            if (o.finished) {
+                if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
+                write_obs(b.terminal_obs, n, i, p, dv, e.y);
+                write_terminal_state(b, n, i, e.y);
+                if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+                if (!p.auto_reset) {
+                    for (int jj = j + 1; jj < k_steps; jj++) {
+                        if (traj_rew) traj_rew[(int64_t)jj * n + i] = 0.0f;
+                        if (traj_done) traj_done[(int64_t)jj * n + i] = 2;
+                    }
+                    live = false;
+                } else
+                    env_reset(p, b, seed, env_offset + i, e);
+            }
+        }
+    }
+    if (loaded) {
+        if (b.reward) b.reward[i] = o.reward;
+        if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
+        b.done[i] = o.finished ? 1 : 0;
+        b.flags[i] = (uint8_t)o.flags;
+        if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
+        if (b.status) b.status[i] = (int8_t)o.status;
+        write_obs(b.obs, n, i, p, dv, e.y);
+        env_store(b, n, i, e);
+    }
+    if (b.stats) stats_steps(b.stats, my_steps);
+}
+
 // Simulator6DOF.step, raw (all-float64) mode
 template <bool kExact>
 __global__ void __launch_bounds__(kThreads, R6_MIN_BLOCKS)
@@ -330,6 +409,7 @@ int enable_all()
     rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, true>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_MLP, false>, smem_mlp_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_MLP, true>, smem_mlp_bytes<R>());
+    rc |= enable_smem(rollout_tc_kernel<R>, smem_tc_bytes<R>());
     return rc;
 }
 int ensure_attributes()
@@ -392,11 +472,14 @@ int launch_rollout(const R6Params *p, const R6Buffers *b, const Derived &dv, int
     } else if (mode == R6_ACT_BUFFER) {
         if (!act_buf) return fail(R6_EINVAL, "act_buf is null%s");
         if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, true, act_buf, smem_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_BUFFER, false, act_buf, smem_bytes<R>());
-    } else if (mode == R6_ACT_MLP) {
+    } else if (mode == R6_ACT_MLP || mode == R6_ACT_MLP_TC) {
         if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
             return fail(R6_EINVAL, "policy weights are null%s");
         m = *mlp;
-        if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_MLP, true, nullptr, smem_mlp_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_MLP, false, nullptr, smem_mlp_bytes<R>());
+        if (mode == R6_ACT_MLP_TC && !exact)
+            rollout_tc_kernel<R><<<g, kThreads, smem_tc_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, k, m, seed, traj_obs,
+                                                                       traj_act, traj_rew, traj_done);
+        else if (exact) R6_LAUNCH_ROLLOUT(R6_ACT_MLP, true, nullptr, smem_mlp_bytes<R>()); else R6_LAUNCH_ROLLOUT(R6_ACT_MLP, false, nullptr, smem_mlp_bytes<R>());
     } else
         return fail(R6_EINVAL, "unsupported action mode%s");
 #undef R6_LAUNCH_ROLLOUT

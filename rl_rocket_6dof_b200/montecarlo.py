@@ -17,7 +17,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .batch import ACT_MLP, Rocket6DOFBatch
+from .batch import ACT_MLP, ACT_MLP_TC, Rocket6DOFBatch
 from . import policy as _policy
 
 HEADER = ["final_position_error", "final_velocity_error", "attitude_error", "angular_velocity_error", "used mass"]
@@ -38,9 +38,10 @@ def dispersion_columns(terminal_state: torch.Tensor) -> Dict[str, torch.Tensor]:
 def run_montecarlo(n_episodes: int, weights: Dict[str, np.ndarray], env_config: Optional[dict] = None,
                    sb3_config: Optional[dict] = None, *, device="cuda", seed: Optional[int] = None,
                    chunk_steps: int = 128, csv_path: Optional[str] = None, ic_table: Optional[np.ndarray] = None,
-                   env_offset: int = 0, num_envs_global: Optional[int] = None) -> dict:
+                   env_offset: int = 0, num_envs_global: Optional[int] = None, tensor_cores: bool = False) -> dict:
     """Returns {"columns": {name: np.ndarray[n]}, "mean": {...}, "std": {...}, "episode_length", "episode_return",
-    "landed", "stats"}.  `std` is the sample standard deviation (pandas' default, ddof=1)."""
+    "landed", "stats"}.  `std` is the sample standard deviation (pandas' default, ddof=1).
+    tensor_cores=True evaluates the policy with R6_ACT_MLP_TC (3xTF32 MMA tiles) instead of float32 FMAs."""
     env = Rocket6DOFBatch(n_episodes, env_config, sb3_config, device=device, seed=seed, auto_reset=False,
                           clip_reward=True, time_limit=True, ic_table=ic_table, env_offset=env_offset,
                           num_envs_global=num_envs_global)
@@ -49,7 +50,7 @@ def run_montecarlo(n_episodes: int, weights: Dict[str, np.ndarray], env_config: 
     max_steps = int(env.params.max_episode_steps) if env.params.max_episode_steps else 1500
     steps = 0
     while steps < max_steps:
-        env.rollout(chunk_steps, ACT_MLP, mlp=w)
+        env.rollout(chunk_steps, ACT_MLP_TC if tensor_cores else ACT_MLP, mlp=w)
         steps += chunk_steps
         if bool(env.done.all()):        # one device->host byte per chunk, not per step
             break

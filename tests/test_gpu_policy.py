@@ -40,6 +40,43 @@ def test_fused_mlp_actions_match_recorded():
     assert f32_ulp_diff(obs, g["obs"][idx - 1][:, :13]).max() <= 1.0
 
 
+def test_tensor_core_mlp_matches_cuda_core_mlp():
+    """R6_ACT_MLP_TC (mma.sync TF32 tiles, 3xTF32 compensation) against the float32 CUDA-core network and the
+    recorded reference actions, on every policy input of the golden closed-loop run; ragged batch size so
+    that the last warp has lanes without an env."""
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import ACT_MLP, ACT_MLP_TC, Rocket6DOFBatch
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts = set(int(s) for s in g["ic_step"])
+    idx = np.array([k for k in range(1, len(g["action"])) if k not in starts])
+    n = len(idx)
+    assert n % 32 != 0
+    ep = env_params()
+    acts = {}
+    for mode in (ACT_MLP, ACT_MLP_TC):
+        env = Rocket6DOFBatch(n, params=ep, device="cuda:0", auto_reset=True, seed=3)
+        st = g["state"][idx - 1]
+        env.set_state(torch.from_numpy(st.astype(np.float32)))
+        env.state.copy_(torch.from_numpy(np.ascontiguousarray(st.T)))
+        traj = env.rollout(1, mode, mlp=policy.to_device(w, env.device), record=True)
+        torch.cuda.synchronize()
+        acts[mode] = traj["act"][0].cpu().numpy()
+        if mode == ACT_MLP_TC:
+            assert f32_ulp_diff(traj["obs"][0].t().cpu().numpy(), g["obs"][idx - 1][:, :13]).max() <= 1.0
+            state_tc = env.state.clone()
+        else:
+            state_cc = env.state.clone()
+    d = np.abs(acts[ACT_MLP_TC] - acts[ACT_MLP]).max()
+    print(f"tensor-core vs CUDA-core policy: max |d action| = {d:.2e}; vs recorded: "
+          f"{np.abs(acts[ACT_MLP_TC] - g['action'][idx]).max():.2e}")
+    assert d <= 2e-6
+    assert np.abs(acts[ACT_MLP_TC] - g["action"][idx]).max() <= 3e-6
+    norm = torch.as_tensor(ep.state_normalizer, device="cuda")[:, None]
+    assert float(((state_tc - state_cc).abs() / norm).max()) <= 1e-7      # one env-step downstream of the actions
+
+
 def test_rollout_mlp_needs_weights():
     from rl_rocket_6dof_b200._lib import R6Error
     from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
@@ -54,7 +91,8 @@ def test_rollout_mlp_needs_weights():
     assert R6Error is not None
 
 
-def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path):
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path, tensor_cores):
     """30 episodes from the reference's own initial conditions, policy in the loop on both sides.
     The loop feeds a float32 network back into the dynamics, so agreement is to the amplification of
     float32 round-off in the actions (SURVEY §7 hard part 8), not to 1e-9: episode lengths within one
@@ -66,7 +104,8 @@ def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path):
     n = len(starts)
     assert g["done"][ends[-1] - 1] or g["truncated"][ends[-1] - 1]
     csv_path = str(tmp_path / "results_montecarlo.csv")
-    res = montecarlo.run_montecarlo(n, w, device="cuda:0", ic_table=g["ic"], csv_path=csv_path, chunk_steps=64)
+    res = montecarlo.run_montecarlo(n, w, device="cuda:0", ic_table=g["ic"], csv_path=csv_path, chunk_steps=64,
+                                    tensor_cores=tensor_cores)
     ref_len = np.array([e - s for s, e in zip(starts, ends)])
     ref_term = np.stack([g["state"][e - 1] for e in ends])
     print("episode length diff:", res["episode_length"] - ref_len)
