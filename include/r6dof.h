@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 7
+#define R6_ABI_VERSION 8
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -207,6 +207,19 @@ int r6_sim_step_raw(double *state, const double *u, const double *m0, const doub
  * c0 t^4 + c2 t^2 + c3 t + c4, one per element (NaN when there is none). */
 int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo,
            void *stream);
+
+/*
+ * Generalised advantage estimation over a recorded rollout, on the device, so that the PPO update of
+ * main_6DOF.py:136 (`model.learn`) can consume r6_rollout's trajectory buffers without a host round trip.
+ * Restates stable-baselines3 1.6.0 `RolloutBuffer.compute_returns_and_advantage` (common/buffers.py; SB3 is a
+ * dependency of the reference, not part of its tree) in float32 with NumPy's operation order:
+ *     nnt_t   = 1 - done[t]                      (done[t] = episode ended at step t = episode_starts[t+1])
+ *     delta_t = rew[t] + gamma * V[t+1] * nnt_t - V[t]          (V[T] = last_values)
+ *     A_t     = delta_t + f32(gamma * lambda) * nnt_t * A_{t+1}  (A_T = 0),   returns = A + V
+ * rew, values, adv, ret: float32 [T][n]; done: uint8 [T][n] (non-zero = ended); last_values: float32 [n].
+ */
+int r6_gae(const float *rew, const float *values, const uint8_t *done, const float *last_values, int32_t T, int64_t n,
+           double gamma, double gae_lambda, float *adv, float *ret, void *stream);
 
 /* Zeroes stats[8] (asynchronously, on the stream). */
 int r6_stats_reset(double *stats, void *stream);

@@ -371,6 +371,28 @@ tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int6
     if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i]);
 }
 
+// GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
+// envs).  HBM-bound: 17 B per (t, env).  No FMA contraction: the float32 roundings are NumPy's.
+__global__ void __launch_bounds__(256)
+gae_kernel(const float *__restrict__ rew, const float *__restrict__ values, const uint8_t *__restrict__ done,
+           const float *__restrict__ last_values, int T, int64_t n, float gamma, float gl, float *__restrict__ adv,
+           float *__restrict__ ret)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float next_v = last_values[i], last = 0.0f;
+    for (int t = T - 1; t >= 0; t--) {
+        const int64_t o = (int64_t)t * n + i;
+        const float v = values[o];
+        const float nnt = done[o] ? 0.0f : 1.0f;
+        const float delta = __fsub_rn(__fadd_rn(rew[o], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v);
+        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+        adv[o] = last;
+        ret[o] = __fadd_rn(last, v);
+        next_v = v;
+    }
+}
+
 // FMA-pipe micro-benchmark: 8 independent chains per thread
 template <typename T>
 __global__ void __launch_bounds__(256) peak_fma_kernel(int iters, double *sink)
@@ -563,6 +585,17 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
     if (n <= 0) return n == 0 ? R6_OK : fail(R6_EINVAL, "n < 0%s");
     tgo_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(c2, c3, c4, c0, n, tgo);
     return check_launch("r6_tgo");
+}
+
+int r6_gae(const float *rew, const float *values, const uint8_t *done, const float *last_values, int32_t T, int64_t n,
+           double gamma, double gae_lambda, float *adv, float *ret, void *stream)
+{
+    if (!rew || !values || !done || !last_values || !adv || !ret) return fail(R6_EINVAL, "null pointer%s");
+    if (T < 0 || n < 0) return fail(R6_EINVAL, "negative size%s");
+    if (T == 0 || n == 0) return R6_OK;
+    gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, values, done, last_values, T, n, (float)gamma,
+                                                                          (float)(gamma * gae_lambda), adv, ret);
+    return check_launch("r6_gae");
 }
 
 int r6_stats_reset(double *stats, void *stream)
