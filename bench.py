@@ -312,6 +312,19 @@ def run_b200(args):
     ms_pol_tc = max_over_ranks(e0.elapsed_time(e1))
     barrier()
 
+    # closed loop as two kernels per env-step (r6_policy + r6_step): what a VecEnv consumer with the policy on
+    # the device runs; 2 launches per step
+    ms_two = {}
+    for tc in (False, True):
+        env.step_policy(W, wdev, tensor_cores=tc)
+        barrier()
+        e0.record(stream)
+        env.step_policy(K, wdev, tensor_cores=tc)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_two[tc] = max_over_ranks(e0.elapsed_time(e1))
+        barrier()
+
     # ---- end to end through the VecEnv fast path (host actions in, host obs/reward/done out) --
     for w in range(W):
         vec.step_host(acts_h[w % R])
@@ -389,6 +402,12 @@ def run_b200(args):
                                         "ms_per_step": ms_pol_tc / KP, "launches": 1,
                                         "actions": "same network as rollout_policy on mma.sync TF32 tiles, 3xTF32 "
                                                    "compensation, one warp = 32 envs, activations register-chained"},
+        "closed_loop_two_kernels": {"value": world * n * K / (ms_two[False] * 1e-3), "unit": UNIT,
+                                    "ms_per_step": ms_two[False] / K, "launches_per_step": 2,
+                                    "actions": "r6_policy (float32 FMA network) then r6_step"},
+        "closed_loop_two_kernels_tensor_cores": {"value": world * n * K / (ms_two[True] * 1e-3), "unit": UNIT,
+                                                 "ms_per_step": ms_two[True] / K, "launches_per_step": 2,
+                                                 "actions": "r6_policy (mma.sync TF32 tiles, 3xTF32) then r6_step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},

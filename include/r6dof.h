@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 8
+#define R6_ABI_VERSION 9
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -207,6 +207,15 @@ int r6_sim_step_raw(double *state, const double *u, const double *m0, const doub
  * c0 t^4 + c2 t^2 + c3 t + c4, one per element (NaN when there is none). */
 int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo,
            void *stream);
+
+/*
+ * The policy alone: actions[i][0:3] = clip(actor(obs[0:13][i]), -1, 1) for n envs, as its own kernel
+ * (model.predict(obs, deterministic=True) of montecarlo_script.py:57-64 / PPO.collect_rollouts).  A closed-loop
+ * VecEnv step is then r6_policy followed by r6_step: the network runs as a uniform, high-occupancy GEMM-chain
+ * kernel instead of inside the divergent integrator.  obs: float32 [>=13][n] component-major (R6Buffers.obs);
+ * actions: float32 [n][3].  tensor_cores = 0: float32 FMAs (R6_ACT_MLP's code); 1: mma.sync TF32 tiles, 3xTF32.
+ */
+int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream);
 
 /*
  * Generalised advantage estimation over a recorded rollout, on the device, so that the PPO update of

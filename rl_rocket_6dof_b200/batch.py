@@ -166,6 +166,28 @@ class Rocket6DOFBatch:
         self.steps_done += int(k)
         return traj
 
+    def policy_actions(self, mlp: dict, *, tensor_cores: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch)."""
+        if out is None:
+            out = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
+        m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.r6_policy(C.byref(m), self.obs.data_ptr(), self.num_envs, int(tensor_cores),
+                                          out.data_ptr(), self._stream()), self.lib)
+        return out
+
+    def step_policy(self, k: int, mlp: dict, *, tensor_cores: bool = False):
+        """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes
+        the actions, the step kernel consumes them — VecEnv semantics (auto-reset as configured).  Faster than the
+        single fused rollout kernel for large batches; `rollout(k, ACT_MLP)` remains for one-episode semantics."""
+        act = getattr(self, "_policy_act", None)
+        if act is None:
+            act = self._policy_act = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
+        for _ in range(int(k)):
+            self.policy_actions(mlp, tensor_cores=tensor_cores, out=act)
+            self.step(act)
+        return self.obs, self.reward, self.done, self.flags
+
     # ------------------------------------------------------------------ state injection / inspection
     def set_state(self, state: torch.Tensor, idx: Optional[torch.Tensor] = None, *, step_count: int = 0):
         """Starts new episodes from given float32 initial conditions [M,14] (already normalised

@@ -371,6 +371,32 @@ tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int6
     if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i]);
 }
 
+// The policy as its own kernel (r6_policy): uniform work, no integrator state => small code, high occupancy.
+// Persistent: the grid is one wave of CTAs, each packs the weights into shared memory ONCE (the gather with its
+// index arithmetic costs as much as one network evaluation) and then walks over its tiles of 128 envs.
+template <bool kTc>
+__global__ void __launch_bounds__(kThreads, kTc ? 3 : 4)
+policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *__restrict__ actions)
+{
+    extern __shared__ double r6_smem[];
+    float *Ws = reinterpret_cast<float *>(r6_smem);
+    const int nW = kTc ? kMlpTcFloats : kMlpFloats;
+    for (int idx = threadIdx.x; idx < nW; idx += kThreads) Ws[idx] = kTc ? mlp_tc_pack_element(mlp, idx) : mlp_pack_element(mlp, idx);
+    __syncthreads();
+    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t i = tile * kThreads + threadIdx.x;
+        float x[kMlpIn], a0, a1, a2;
+#pragma unroll
+        for (int c = 0; c < kMlpIn; c++) x[c] = i < n ? obs[(int64_t)c * n + i] : 0.0f;
+        if (kTc) mlp_policy_tc(Ws, Ws + kMlpTcFloats + (threadIdx.x >> 5) * (16 * 33), x, a0, a1, a2);
+        else mlp_policy(Ws, x, a0, a1, a2);
+        if (i < n) { actions[3 * i] = a0; actions[3 * i + 1] = a1; actions[3 * i + 2] = a2; }
+    }
+}
+constexpr int kSmemPolicyTc = (r6::kMlpTcFloats + (kThreads / 32) * 16 * 33) * (int)sizeof(float);
+constexpr int kSmemPolicy = r6::kMlpFloats * (int)sizeof(float);
+
 // GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
 // envs).  HBM-bound: 17 B per (t, env).  No FMA contraction: the float32 roundings are NumPy's.
 __global__ void __launch_bounds__(256)
@@ -441,6 +467,8 @@ int ensure_attributes()
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(R6_ECUDA, "cudaGetDevice failed%s");
     if (dev == device_done) return R6_OK;
     int rc = enable_all<double>() | enable_all<float>();
+    rc |= enable_smem(policy_kernel<true>, kSmemPolicyTc);
+    rc |= enable_smem(policy_kernel<false>, kSmemPolicy);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -585,6 +613,29 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
     if (n <= 0) return n == 0 ? R6_OK : fail(R6_EINVAL, "n < 0%s");
     tgo_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(c2, c3, c4, c0, n, tgo);
     return check_launch("r6_tgo");
+}
+
+int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream)
+{
+    if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
+        return fail(R6_EINVAL, "policy weights are null%s");
+    if (!obs || !actions) return fail(R6_EINVAL, "null pointer%s");
+    if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (n == 0) return R6_OK;
+    int rc = ensure_attributes();
+    if (rc) return rc;
+    // one resident wave: SM count x resident CTAs per SM (3 with the tensor-core tiles' registers, 4 otherwise)
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    const int64_t wave = (int64_t)sm_count * (tensor_cores ? 3 : 4);
+    const unsigned g = (unsigned)(blocks_for(n) < wave ? blocks_for(n) : wave);
+    if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
+    else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
+    return check_launch("r6_policy");
 }
 
 int r6_gae(const float *rew, const float *values, const uint8_t *done, const float *last_values, int32_t T, int64_t n,

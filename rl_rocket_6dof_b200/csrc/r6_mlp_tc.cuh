@@ -10,7 +10,7 @@
 // fragment of the next (after a free permutation of the weight rows, below) and the warps of a CTA,
 // which finish their adaptive integration at different times, never have to meet.
 //
-// Precision: 3xTF32 error compensation — every operand is split x = hi + lo with hi = rna_tf32(x), and
+// Precision: 3xTF32 error compensation — every operand is split x = hi + lo with hi = round_tf32(x), and
 // hi*hi + lo*hi + hi*lo is accumulated in float32, which restores ~float32 accuracy (the dropped lo*lo
 // term is 2^-22 relative).  tanh is evaluated in float32 on the exp2 / rcp units.
 // Measured against the float32 CUDA-core network (R6_ACT_MLP): |d action| <= 2e-6 (tests/test_gpu_policy.py).
@@ -59,10 +59,13 @@ __device__ __forceinline__ float mlp_tc_pack_element(const R6Mlp &m, int idx)
 }
 
 struct Split { uint32_t hi, lo; };
+// x = hi + lo with hi the nearest TF32 (10-bit mantissa) value, by integer arithmetic: add half an ulp of the
+// 13 dropped bits and mask them (3 instructions; sm_100a has no hardware cvt.rna.tf32 and ptxas expands that
+// into a ~7-instruction sequence with branches — it was 45 % of this kernel).  Finite inputs only.
 __device__ __forceinline__ Split tf32_split(float x)
 {
     Split s;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s.hi) : "f"(x));
+    s.hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     s.lo = __float_as_uint(x - __uint_as_float(s.hi));
     return s;
 }

@@ -77,6 +77,38 @@ def test_tensor_core_mlp_matches_cuda_core_mlp():
     assert float(((state_tc - state_cc).abs() / norm).max()) <= 1e-7      # one env-step downstream of the actions
 
 
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_policy_kernel_and_two_kernel_closed_loop(tensor_cores):
+    """r6_policy on the recorded observations, then r6_policy + r6_step chained == the fused rollout kernel."""
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import ACT_MLP, ACT_MLP_TC, Rocket6DOFBatch
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts = set(int(s) for s in g["ic_step"])
+    idx = np.array([k for k in range(1, len(g["action"])) if k not in starts])
+    ep = env_params()
+    env = Rocket6DOFBatch(len(idx), params=ep, device="cuda:0", seed=3)
+    wd = policy.to_device(w, env.device)
+    env.obs.copy_(torch.from_numpy(np.ascontiguousarray(g["obs"][idx - 1].T)))
+    a = env.policy_actions(wd, tensor_cores=tensor_cores).cpu().numpy()
+    assert np.abs(a - g["action"][idx]).max() <= 3e-6
+    # closed loop, VecEnv semantics: 2k launches vs one fused launch, same seeds => same episodes
+    n, k = 3000, 150
+    x = Rocket6DOFBatch(n, params=ep, device="cuda:0", seed=17)
+    y = Rocket6DOFBatch(n, params=ep, device="cuda:0", seed=17)
+    x.reset(); y.reset()
+    x.step_policy(k, wd, tensor_cores=tensor_cores)
+    y.rollout(k, ACT_MLP_TC if tensor_cores else ACT_MLP, mlp=wd)
+    torch.cuda.synchronize()
+    assert torch.equal(x.episode_id, y.episode_id) and torch.equal(x.step_count, y.step_count)
+    norm = torch.as_tensor(ep.state_normalizer, device="cuda")[:, None]
+    # same network code in both kernels; nvcc may contract the surrounding arithmetic differently
+    assert float(((x.state - y.state).abs() / norm).max()) <= 1e-6
+    sx, sy = x.stats.cpu().numpy(), y.stats.cpu().numpy()
+    assert np.array_equal(sx[[0, 2, 3, 4, 5, 6, 7]], sy[[0, 2, 3, 4, 5, 6, 7]])
+
+
 def test_rollout_mlp_needs_weights():
     from rl_rocket_6dof_b200._lib import R6Error
     from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
