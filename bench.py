@@ -315,7 +315,7 @@ def run_b200(args):
     # closed loop as two kernels per env-step (r6_policy + r6_step): what a VecEnv consumer with the policy on
     # the device runs; 2 launches per step
     ms_two = {}
-    for tc in (False, True):
+    for tc in (0, 1, 2):
         env.step_policy(W, wdev, tensor_cores=tc)
         barrier()
         e0.record(stream)
@@ -402,12 +402,16 @@ def run_b200(args):
                                         "ms_per_step": ms_pol_tc / KP, "launches": 1,
                                         "actions": "same network as rollout_policy on mma.sync TF32 tiles, 3xTF32 "
                                                    "compensation, one warp = 32 envs, activations register-chained"},
-        "closed_loop_two_kernels": {"value": world * n * K / (ms_two[False] * 1e-3), "unit": UNIT,
-                                    "ms_per_step": ms_two[False] / K, "launches_per_step": 2,
+        "closed_loop_two_kernels": {"value": world * n * K / (ms_two[0] * 1e-3), "unit": UNIT,
+                                    "ms_per_step": ms_two[0] / K, "launches_per_step": 2,
                                     "actions": "r6_policy (float32 FMA network) then r6_step"},
-        "closed_loop_two_kernels_tensor_cores": {"value": world * n * K / (ms_two[True] * 1e-3), "unit": UNIT,
-                                                 "ms_per_step": ms_two[True] / K, "launches_per_step": 2,
+        "closed_loop_two_kernels_tensor_cores": {"value": world * n * K / (ms_two[1] * 1e-3), "unit": UNIT,
+                                                 "ms_per_step": ms_two[1] / K, "launches_per_step": 2,
                                                  "actions": "r6_policy (mma.sync TF32 tiles, 3xTF32) then r6_step"},
+        "closed_loop_two_kernels_tcgen05": {"value": world * n * K / (ms_two[2] * 1e-3), "unit": UNIT,
+                                            "ms_per_step": ms_two[2] / K, "launches_per_step": 2,
+                                            "actions": "r6_policy (tcgen05.mma kind::tf32, TMEM accumulators, single-pass TF32: "
+                                                       "|d action| ~1e-3) then r6_step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},

@@ -213,7 +213,9 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
  * (model.predict(obs, deterministic=True) of montecarlo_script.py:57-64 / PPO.collect_rollouts).  A closed-loop
  * VecEnv step is then r6_policy followed by r6_step: the network runs as a uniform, high-occupancy GEMM-chain
  * kernel instead of inside the divergent integrator.  obs: float32 [>=13][n] component-major (R6Buffers.obs);
- * actions: float32 [n][3].  tensor_cores = 0: float32 FMAs (R6_ACT_MLP's code); 1: mma.sync TF32 tiles, 3xTF32.
+ * actions: float32 [n][3].  tensor_cores = 0: float32 FMAs (R6_ACT_MLP's code); 1: mma.sync TF32 tiles with 3xTF32
+ * compensation (|d action| <= 2e-6 vs mode 0); 2: tcgen05.mma kind::tf32 with TMEM accumulators, single pass
+ * (fast mode, |d action| ~1e-3 vs mode 0).
  */
 int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream);
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Driver for profiling r6_policy alone: python profiles/run_policy_kernel.py [tc|cc] [envs]"""
+"""Driver for profiling r6_policy alone: python profiles/run_policy_kernel.py [cc|tc|tcgen05] [envs]"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rl_rocket_6dof_b200 import policy  # noqa: E402
 from rl_rocket_6dof_b200.batch import Rocket6DOFBatch  # noqa: E402
 
-tc = len(sys.argv) < 2 or sys.argv[1] == "tc"
+tc = {"cc": 0, "tc": 1, "tcgen05": 2}[sys.argv[1] if len(sys.argv) > 1 else "tc"]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 w = policy.to_device(policy.load_npz(os.path.join(root, "tests", "golden", "policy_cl.npz")), "cuda:0")

@@ -166,8 +166,10 @@ class Rocket6DOFBatch:
         self.steps_done += int(k)
         return traj
 
-    def policy_actions(self, mlp: dict, *, tensor_cores: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch)."""
+    def policy_actions(self, mlp: dict, *, tensor_cores=False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch).
+        tensor_cores: False / 0 = float32 FMA network; True / 1 = mma.sync 3xTF32 tiles (faithful to 2e-6);
+        2 = tcgen05 + TMEM single-pass TF32 (fast mode, ~1e-3)."""
         if out is None:
             out = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
         m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
@@ -176,7 +178,7 @@ class Rocket6DOFBatch:
                                           out.data_ptr(), self._stream()), self.lib)
         return out
 
-    def step_policy(self, k: int, mlp: dict, *, tensor_cores: bool = False):
+    def step_policy(self, k: int, mlp: dict, *, tensor_cores=False):
         """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes
         the actions, the step kernel consumes them — VecEnv semantics (auto-reset as configured).  Faster than the
         single fused rollout kernel for large batches; `rollout(k, ACT_MLP)` remains for one-episode semantics."""

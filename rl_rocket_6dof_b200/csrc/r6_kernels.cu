@@ -14,6 +14,7 @@
 
 #include "r6_core.cuh"
 #include "r6_mlp_tc.cuh"
+#include "r6_mlp_tcgen05.cuh"
 
 namespace {
 
@@ -397,6 +398,95 @@ policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *
 constexpr int kSmemPolicyTc = (r6::kMlpTcFloats + (kThreads / 32) * 16 * 33) * (int)sizeof(float);
 constexpr int kSmemPolicy = r6::kMlpFloats * (int)sizeof(float);
 
+// The policy on tcgen05 / TMEM (r6_policy tensor_cores = 2, fast single-pass TF32 mode): see r6_mlp_tcgen05.cuh.
+__global__ void __launch_bounds__(tc5::kTile, 2)
+policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *__restrict__ actions)
+{
+    using namespace tc5;
+    extern __shared__ double r6_smem[];
+    char *S = reinterpret_cast<char *>(r6_smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // ---- one-time per CTA: weights (TF32-rounded) into canonical K-major tiles, biases, barrier, TMEM ----
+    for (int idx = tid; idx < 128 * 16; idx += kTile) {
+        const int r = idx >> 4, k = idx & 15;
+        *reinterpret_cast<float *>(S + kOffW0 + tile_off(r, k, 16)) = k < kMlpIn ? round_tf32(mlp.w0[r * kMlpIn + k]) : 0.0f;
+    }
+    for (int idx = tid; idx < 64 * 128; idx += kTile) {
+        const int r = idx >> 7, k = idx & 127;
+        *reinterpret_cast<float *>(S + kOffW1 + tile_off(r, k, 128)) = round_tf32(mlp.w1[r * kMlpH0 + k]);
+    }
+    for (int idx = tid; idx < 16 * 64; idx += kTile) {
+        const int r = idx >> 6, k = idx & 63;
+        *reinterpret_cast<float *>(S + kOffW2 + tile_off(r, k, 64)) = r < kMlpOut ? round_tf32(mlp.w2[r * kMlpH1 + k]) : 0.0f;
+    }
+    float *bias = reinterpret_cast<float *>(S + kOffBias);
+    bias[tid] = mlp.b0[tid];
+    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
+    if (tid < 4) bias[192 + tid] = tid < kMlpOut ? mlp.b2[tid] : 0.0f;
+    const uint32_t bar = smem_u32(S + kOffBar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtr)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtr);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t aX = smem_u32(S + kOffX), aH = smem_u32(S + kOffH);
+    const uint32_t aW0 = smem_u32(S + kOffW0), aW1 = smem_u32(S + kOffW1), aW2 = smem_u32(S + kOffW2);
+    uint32_t phase = 0;
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t i = tile * kTile + tid;
+        // ---- observations of this thread's env -> row `tid` of the X tile ----
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++) {
+            float4 v;
+            v.x = (4 * kc + 0 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 0) * n + i]) : 0.0f;
+            v.y = (4 * kc + 1 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 1) * n + i]) : 0.0f;
+            v.z = (4 * kc + 2 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 2) * n + i]) : 0.0f;
+            v.w = (4 * kc + 3 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 3) * n + i]) : 0.0f;
+            *reinterpret_cast<float4 *>(S + kOffX + tile_off(tid, 4 * kc, 16)) = v;
+        }
+        fence_async_smem(); fence_before(); __syncthreads();
+        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD0, aX, 512, aW0, 512, 2, 128, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
+        epilogue_to_h(tmem_row, kColD0, bias, S + kOffH, tid);
+        fence_async_smem(); fence_before(); __syncthreads();
+        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD1, aH, 2048, aW1, 4096, 8, 64, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- second half ----
+        epilogue_to_h(tmem_row, kColD0 + 64, bias + 64, S + kOffH, tid);
+        fence_async_smem(); fence_before(); __syncthreads();
+        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD1, aH, 2048, aW1 + 2048, 4096, 8, 64, true); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 1 -> output layer ----
+        epilogue_to_h(tmem_row, kColD1, bias + 128, S + kOffH, tid);
+        fence_async_smem(); fence_before(); __syncthreads();
+        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD2, aH, 2048, aW2, 2048, 8, 16, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        {
+            float v[32];
+            tmem_ld32(tmem_row + kColD2, v);
+            if (i < n) {
+                actions[3 * i] = fminf(fmaxf(v[0] + bias[192], -1.0f), 1.0f);
+                actions[3 * i + 1] = fminf(fmaxf(v[1] + bias[193], -1.0f), 1.0f);
+                actions[3 * i + 2] = fminf(fmaxf(v[2] + bias[194], -1.0f), 1.0f);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
 // GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
 // envs).  HBM-bound: 17 B per (t, env).  No FMA contraction: the float32 roundings are NumPy's.
 __global__ void __launch_bounds__(256)
@@ -469,6 +559,7 @@ int ensure_attributes()
     int rc = enable_all<double>() | enable_all<float>();
     rc |= enable_smem(policy_kernel<true>, kSmemPolicyTc);
     rc |= enable_smem(policy_kernel<false>, kSmemPolicy);
+    rc |= enable_smem(policy_tc5_kernel, tc5::kSmemBytes);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -631,9 +722,11 @@ int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_core
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
-    const int64_t wave = (int64_t)sm_count * (tensor_cores ? 3 : 4);
+    if (tensor_cores < 0 || tensor_cores > 2) return fail(R6_EINVAL, "tensor_cores must be 0, 1 or 2%s");
+    const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
     const unsigned g = (unsigned)(blocks_for(n) < wave ? blocks_for(n) : wave);
-    if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
+    if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
+    else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
     return check_launch("r6_policy");
 }

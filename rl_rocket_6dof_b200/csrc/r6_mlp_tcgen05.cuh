@@ -1,0 +1,144 @@
+// r6_mlp_tcgen05.cuh — the policy MLP (13 -> 128 -> 64 -> 3, tanh) on the 5th-generation tensor cores:
+// tcgen05.mma (kind::tf32, M = 128 envs per CTA, operands in shared memory, accumulators in TMEM), tcgen05.ld for
+// the epilogues, one elected thread issuing the MMAs, mbarrier completion.  This is the FAST policy mode of
+// r6_policy (tensor_cores = 2): single-pass TF32, |d action| ~1e-3 against the float32 network, for rollouts where
+// the policy's own exploration noise dwarfs that; the faithful modes are the FMA network and the 3xTF32 MMA tiles
+// (r6_mlp_tc.cuh).  It exists as its own uniform kernel because a tcgen05 MMA is a CTA-wide operation: all 128
+// rows of the A tile must be in shared memory and every thread meets at a barrier per layer, which the divergent
+// integrator cannot afford but a dedicated policy kernel can.
+//
+// Per tile of 128 envs (thread t <-> env row t <-> TMEM lane t):
+//   X [128x16]  -> smem  | MMA  D0[128x128] = X  W0^T           (2 x K8)
+//   D0 cols  0..63  -> +b0, tanh -> Hs [128x64] | MMA D1[128x64]  = Hs W1[:,  0: 64]^T   (8 x K8)
+//   D0 cols 64..127 -> +b0, tanh -> Hs          | MMA D1        += Hs W1[:, 64:128]^T   (8 x K8)
+//   D1 -> +b1, tanh -> Hs [128x64]              | MMA D2[128x16] = Hs W2^T              (8 x K8)
+//   D2 cols 0..2 -> +b2, clip -> actions
+// The 128-wide hidden layer is fed to layer 1 in two K-halves so that the A staging tile is 32 KB instead of 64:
+// 84 KB of shared memory and 256 TMEM columns per CTA => two CTAs per SM, one running MMAs while the other is in
+// an epilogue.
+//
+// Shared-memory operand layout (both operands K-major, SWIZZLE_NONE "interleaved" canonical layout): element
+// (row r, k) of a tile with K_tot columns lives at byte  (r % 8) * 16 + (r / 8) * SBO + (k / 4) * 128 + (k % 4) * 4,
+// SBO = (K_tot / 4) * 128: 8-row x 16-byte core matrices, consecutive K chunks 128 B apart (LBO), 8-row groups SBO
+// apart.  One MMA consumes K = 8 (two chunks), so k-block kb starts 256 B further.
+#pragma once
+
+#include <stdint.h>
+
+#include "r6_core.cuh"
+
+namespace r6 {
+namespace tc5 {
+
+constexpr int kTile = 128;                       // envs per CTA tile = MMA M
+constexpr uint32_t kTmemCols = 256;              // D0: [0,128)  D1: [128,192)  D2: [192,208)
+constexpr uint32_t kColD0 = 0, kColD1 = 128, kColD2 = 192;
+// byte offsets inside the dynamic shared memory block
+constexpr int kOffW0 = 0;                        // [128][16]   8 KB
+constexpr int kOffW1 = kOffW0 + 128 * 16 * 4;    // [64][128]  32 KB
+constexpr int kOffW2 = kOffW1 + 64 * 128 * 4;    // [16][64]    4 KB
+constexpr int kOffX = kOffW2 + 16 * 64 * 4;      // [128][16]   8 KB
+constexpr int kOffH = kOffX + 128 * 16 * 4;      // [128][64]  32 KB
+constexpr int kOffBias = kOffH + 128 * 64 * 4;   // b0[128] b1[64] b2[4]
+constexpr int kOffBar = kOffBias + (128 + 64 + 4) * 4;
+constexpr int kOffTmemPtr = kOffBar + 8;
+constexpr int kSmemBytes = kOffTmemPtr + 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int tile_off(int r, int k, int ktot) { return (r & 7) * 16 + (r >> 3) * (ktot * 32) + (k >> 2) * 128 + (k & 3) * 4; }
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
+// version 1 (Blackwell), SWIZZLE_NONE
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t instr_desc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// float32 tanh, ~1.5e-7 absolute error (exp2 / rcp units)
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float e, r;
+    const float z = fminf(fabsf(x), 40.0f) * 2.8853900817779268f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return copysignf(fmaf(-2.0f, r, 1.0f), x);
+}
+
+// tanh(D[:, col0 .. col0+63] + bias) of this thread's row -> staging tile Hs [128][64] (TF32-rounded)
+__device__ __forceinline__ void epilogue_to_h(uint32_t tmem_row, uint32_t col0, const float *bias, char *Hs, int row)
+{
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_row + col0 + cc, v);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+            float4 h;
+            h.x = round_tf32(tanh_fast(v[q] + bias[cc + q]));
+            h.y = round_tf32(tanh_fast(v[q + 1] + bias[cc + q + 1]));
+            h.z = round_tf32(tanh_fast(v[q + 2] + bias[cc + q + 2]));
+            h.w = round_tf32(tanh_fast(v[q + 3] + bias[cc + q + 3]));
+            *reinterpret_cast<float4 *>(Hs + tile_off(row, cc + q, 64)) = h;
+        }
+    }
+}
+
+// issue nk K-blocks of D[tmem] (+)= A[a_base ..] B[b_base ..]^T ; both tiles advance 256 B per K-block
+__device__ __forceinline__ void issue_mmas(uint32_t d_tmem, uint32_t a_base, uint32_t a_sbo, uint32_t b_base, uint32_t b_sbo,
+                                           int nk, int n, bool accumulate_first)
+{
+    const uint32_t idesc = instr_desc(n);
+    for (int kb = 0; kb < nk; kb++)
+        mma_tf32(d_tmem, smem_desc(a_base + kb * 256, 128, a_sbo), smem_desc(b_base + kb * 256, 128, b_sbo), idesc,
+                 accumulate_first || kb > 0);
+}
+
+}  // namespace tc5
+}  // namespace r6

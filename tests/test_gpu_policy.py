@@ -109,6 +109,44 @@ def test_policy_kernel_and_two_kernel_closed_loop(tensor_cores):
     assert np.array_equal(sx[[0, 2, 3, 4, 5, 6, 7]], sy[[0, 2, 3, 4, 5, 6, 7]])
 
 
+def test_tcgen05_policy_fast_mode():
+    """r6_policy tensor_cores = 2 (tcgen05.mma kind::tf32, TMEM accumulators, single pass): its own bound — TF32
+    operands carry 2^-11 relative rounding, so actions agree with the float32 network to ~1e-3 (asserted 5e-3),
+    ragged batch, and a closed loop driven by it has the same episode statistics to within sampling noise."""
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts = set(int(s) for s in g["ic_step"])
+    idx = np.array([k for k in range(1, len(g["action"])) if k not in starts])
+    ep = env_params()
+    env = Rocket6DOFBatch(len(idx), params=ep, device="cuda:0", seed=3)
+    assert len(idx) % 128 != 0
+    wd = policy.to_device(w, env.device)
+    env.obs.copy_(torch.from_numpy(np.ascontiguousarray(g["obs"][idx - 1].T)))
+    a2 = env.policy_actions(wd, tensor_cores=2).cpu().numpy()
+    a0 = env.policy_actions(wd, tensor_cores=0).cpu().numpy()
+    d = np.abs(a2 - a0)
+    print(f"tcgen05 TF32 policy vs float32 network: max |d action| {d.max():.2e}, mean {d.mean():.2e}")
+    assert d.max() <= 5e-3 and d.mean() <= 1e-3 and np.all(np.abs(a2) <= 1)
+    # repeated launches (TMEM alloc / dealloc, barrier phases) are stable and deterministic
+    for _ in range(3):
+        assert np.array_equal(env.policy_actions(wd, tensor_cores=2).cpu().numpy(), a2)
+    stats = {}
+    for mode in (0, 2):
+        x = Rocket6DOFBatch(8192, params=ep, device="cuda:0", seed=23)
+        x.reset()
+        x.step_policy(400, wd, tensor_cores=mode)
+        torch.cuda.synchronize()
+        stats[mode] = x.stats_dict()
+    s0, s2 = stats[0], stats[2]
+    print("closed loop fp32:", s0, "\nclosed loop tcgen05:", s2)
+    assert abs(s0["episodes"] - s2["episodes"]) <= 0.01 * s0["episodes"]
+    assert abs(s0["mean_length"] - s2["mean_length"]) <= 0.01 * s0["mean_length"]
+    assert abs(s0["mean_return"] - s2["mean_return"]) <= 0.02 * abs(s0["mean_return"]) + 0.05
+
+
 def test_rollout_mlp_needs_weights():
     from rl_rocket_6dof_b200._lib import R6Error
     from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
