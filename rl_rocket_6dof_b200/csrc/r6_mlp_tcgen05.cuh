@@ -101,14 +101,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// float32 tanh, ~1.5e-7 absolute error (exp2 / rcp units)
+// tanh on the MUFU unit (tanh.approx.f32, relative error 2^-11): the same precision class as the TF32 operands it
+// is rounded to right afterwards, one XU instruction instead of two plus five FP32 ones (the epilogue of this
+// kernel is bound by the XU pipe).
 __device__ __forceinline__ float tanh_fast(float x)
 {
-    float e, r;
-    const float z = fminf(fabsf(x), 40.0f) * 2.8853900817779268f;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return copysignf(fmaf(-2.0f, r, 1.0f), x);
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // tanh(D[:, col0 .. col0+63] + bias) of this thread's row -> staging tile Hs [128][64] (TF32-rounded)
