@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 9
+#define R6_ABI_VERSION 10
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -143,6 +143,8 @@ typedef struct R6Buffers {
     int64_t ic_table_len;
     int64_t n_global;       /* total envs over all shards (ic_table indexing) */
     double *stats;          /* [8] nullable: R6_S_* accumulators */
+    uint8_t *scratch;       /* [2][n] nullable DEVICE bytes: when given, r6_step runs as two kernels (integrator | reward,
+                               flags, reset, observation) that hand the solver status / attempt count through it */
 } R6Buffers;
 
 /* Weights of the SB3 MlpPolicy actor (net_arch [128, 64], tanh), float32 row-major [out][in]. */

@@ -12,7 +12,7 @@ from .params import R6Params
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libr6dof.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 u8p = C.c_void_p
 
@@ -29,6 +29,7 @@ class R6Buffers(C.Structure):
         ("t_table", C.c_void_p), ("ic_table", C.c_void_p),
         ("ic_table_len", C.c_int64), ("n_global", C.c_int64),
         ("stats", C.c_void_p),
+        ("scratch", C.c_void_p),
     ]
 
 

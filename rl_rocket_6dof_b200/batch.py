@@ -8,6 +8,7 @@ C ABI (include/r6dof.h) on the current torch stream.  torch is plumbing only (al
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -32,7 +33,8 @@ class Rocket6DOFBatch:
                  clip_reward: bool = True, time_limit: bool = True, env_offset: int = 0,
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
                  ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
-                 precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None):
+                 precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None,
+                 split_step: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -75,6 +77,10 @@ class Rocket6DOFBatch:
             self.terminal_state = torch.zeros(14, n, dtype=sdt, device=dev)
             self.ep_info = torch.zeros(2, n, dtype=f32, device=dev)
             self.stats = torch.zeros(8, dtype=f64, device=dev)
+            if split_step is None:
+                split_step = os.environ.get("R6_SPLIT_STEP", "1") != "0"
+            # r6_step as two kernels (integrator | post-step) needs 2 bytes of device scratch per env
+            self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
             self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
             self.nattempts = torch.zeros(n, dtype=torch.uint8, device=dev) if (debug_buffers or record_attempts) else None
@@ -102,6 +108,7 @@ class Rocket6DOFBatch:
         b.ic_table_len = 0 if self.ic_table is None else self.ic_table.shape[0]
         b.n_global = self.num_envs_global
         b.stats = ptr(self.stats)
+        b.scratch = ptr(self.scratch)
         return b
 
     def _stream(self) -> int:

@@ -1304,25 +1304,42 @@ R6_HD_NOINLINE double vertical_attitude_term(double q0, double weight)
     return fmin(fmax(2 * deg * weight, -10.0), 10.0);
 }
 
-// One Rocket6DOF.step on the registers of `e` (no reset here).  R = double: the parity path, integrated
-// on the absolute simulator clock t_table[k] like the reference.  R = float: the dynamics are autonomous, so
-// the step is integrated on the local clock [0, dt] (a float32 absolute time would waste its mantissa
-// on the 150 s range); reward / flags are then evaluated by the same float64 code on the widened state.
+// One Rocket6DOF.step on the registers of `e` (no reset here), in two halves so that the step can also run as two
+// kernels (integrate | reward, flags, reset, observation).  R = double: the parity path, integrated on the absolute
+// simulator clock t_table[k] like the reference.  R = float: the dynamics are autonomous, so the step is
+// integrated on the local clock [0, dt] (a float32 absolute time would waste its mantissa on the 150 s range);
+// reward / flags are then evaluated by the same float64 code on the widened state.
+//
+// First half: Simulator6DOF.step (simulator.py:69-104) — action de-normalisation, solve_ivp, quaternion renorm.
 template <bool kExact, class KS, class R>
-R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restrict__ t_table, EnvT<R> &e, float a0,
-                    float a1, float a2, StepOut &o, KS &K)
+R6_HD void env_integrate(const R6Params &p, const double *__restrict__ t_table, R *y, float m0, int k, float a0, float a1,
+                         float a2, KS &K, int &status, int &natt)
 {
     float u0, u1, u2;
     denormalize_action(p, a0, a1, a2, u0, u1, u2);
     StepConstT<R> c;
-    consts_env_mode(c, e.m0, u0, u1, u2, e.y[10]);
+    consts_env_mode(c, m0, u0, u1, u2, y[10]);
     R t = 0;
     if constexpr (sizeof(R) == 8) {
-        const int kk = e.k < p.n_t ? e.k : p.n_t - 1;
+        const int kk = k < p.n_t ? k : p.n_t - 1;
         t = (R)t_table[kk];
     }
-    o.status = integrate<kExact>(c, e.y, t, (R)p.dt, o.natt, K);
-    normalize_quat(e.y);
+    status = integrate<kExact>(c, y, t, (R)p.dt, natt, K);
+    normalize_quat(y);
+}
+
+// Second half: rocket_env.py:206-231 on the post-step state + the make_env() / reward wrappers.  e.k is the step
+// index BEFORE this step (incremented here).
+template <class R>
+R6_HD void env_post(const R6Params &p, const Derived &dv, EnvT<R> &e, float a0, float a1, float a2, int status, int natt,
+                    StepOut &o)
+{
+    float u0, u1, u2;
+    denormalize_action(p, a0, a1, a2, u0, u1, u2);
+    StepConstT<R> c;
+    consts_env_mode(c, e.m0, u0, u1, u2, e.y[10]);      // only the body-frame thrust is used below (w0 is conserved)
+    o.status = status;
+    o.natt = natt;
     e.k += 1;
     if constexpr (sizeof(R) == 8) {
         post_step(p, dv.at, c, reinterpret_cast<const double *>(e.y), u2, e.v0, o.status, o.post);
@@ -1355,6 +1372,15 @@ R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restri
     o.flags = fl;
     o.finished = done || trunc;
     e.ep_return += r;
+}
+
+template <bool kExact, class KS, class R>
+R6_HD void env_step(const R6Params &p, const Derived &dv, const double *__restrict__ t_table, EnvT<R> &e, float a0,
+                    float a1, float a2, StepOut &o, KS &K)
+{
+    int status, natt;
+    env_integrate<kExact>(p, t_table, e.y, e.m0, e.k, a0, a1, a2, K, status, natt);
+    env_post(p, dv, e, a0, a1, a2, status, natt, o);
 }
 
 }  // namespace r6

@@ -192,6 +192,73 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
 }
 
+// The same env-step as two kernels (used by r6_step when R6Buffers.scratch is given): the divergent, register- and
+// shared-memory-hungry integrator on its own, with a hot instruction footprint that fits the instruction cache, and
+// a uniform post-step kernel (reward, flags, wrappers, statistics, auto-reset, observation) without stage storage
+// that runs at twice the occupancy.  Costs one extra read of the state (+128 B per env-step, HBM is at 10 %).
+template <class R, bool kExact>
+__global__ void __launch_bounds__(kThreads, min_blocks<R>())
+integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    KStore<R> K = make_kstore<R>();
+    if (i >= n) return;
+    R *state = reinterpret_cast<R *>(b.state);
+    R y[14];
+#pragma unroll
+    for (int c = 0; c < 14; c++) y[c] = state[(int64_t)c * n + i];
+    const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+    int status, natt;
+    env_integrate<kExact>(p, b.t_table, y, b.m0[i], b.step_count[i], a0, a1, a2, K, status, natt);
+#pragma unroll
+    for (int c = 0; c < 14; c++) state[(int64_t)c * n + i] = y[c];
+    b.scratch[i] = (uint8_t)(int8_t)status;
+    b.scratch[n + i] = (uint8_t)natt;
+}
+
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
+            const float *__restrict__ actions, uint64_t seed)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) {
+        EnvT<R> e;
+        env_load(b, n, i, e);
+        const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+        StepOut o;
+        env_post(p, dv, e, a0, a1, a2, (int)(int8_t)b.scratch[i], (int)b.scratch[n + i], o);
+        if (b.reward) b.reward[i] = o.reward;
+        if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
+        b.done[i] = o.finished ? 1 : 0;
+        b.flags[i] = (uint8_t)o.flags;
+        if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
+        if (b.status) b.status[i] = (int8_t)o.status;
+        if (b.reward_terms) {
+#pragma unroll
+            for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
+        }
+        bool reset = false;
+        if (o.finished) {
+            if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
+            if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+            if (p.auto_reset) {
+                write_obs(b.terminal_obs, n, i, p, dv, e.y);
+                write_terminal_state(b, n, i, e.y);
+                env_reset(p, b, seed, env_offset + i, e);
+                reset = true;
+            }
+        }
+        write_obs(b.obs, n, i, p, dv, e.y);
+        if (reset) env_store(b, n, i, e);
+        else {                                   // the integrator already stored the state
+            b.step_count[i] = e.k;
+            b.ep_return[i] = e.ep_return;
+        }
+    }
+    if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
+}
+
 // k fused steps, state in registers; actions from Philox, a [k][n][3] buffer or the fused policy MLP.
 // p.auto_reset != 0: finished envs restart (VecEnv semantics).  p.auto_reset == 0: an env that finishes
 // is left frozen with done = 1 and its terminal state / observation recorded (evaluate_policy /
@@ -541,6 +608,8 @@ int enable_all()
     int rc = 0;
     rc |= enable_smem(step_kernel<R, false>, smem_bytes<R>());
     rc |= enable_smem(step_kernel<R, true>, smem_bytes<R>());
+    rc |= enable_smem(integrate_kernel<R, false>, smem_bytes<R>());
+    rc |= enable_smem(integrate_kernel<R, true>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, false>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, true>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, false>, smem_bytes<R>());
@@ -593,6 +662,12 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
                  const float *actions, uint64_t seed, cudaStream_t s)
 {
     const unsigned g = (unsigned)blocks_for(n);
+    if (b->scratch != nullptr) {
+        if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, n, actions);
+        else integrate_kernel<R, true><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, n, actions);
+        post_kernel<R><<<g, kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed);
+        return;
+    }
     if (p->dt <= kMaxDtSeries) step_kernel<R, false><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
     else step_kernel<R, true><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
 }
