@@ -5,7 +5,8 @@
 
 A "step" is one Rocket6DOF env-step for every env of the batch (workload: BASELINE.json configs[2],
 2^20 envs per GPU, uniform random actions, auto-reset on).  Rank 0 prints ONE JSON line:
-  value      whole-job env-steps/s, one r6_step launch per env-step, actions already in HBM
+  value      whole-job env-steps/s, one r6_step call (two kernel launches: integrator | post-step) per env-step,
+             actions already in HBM
   e2e        the same through Rocket6DOFVecEnv.step_host: pinned-host actions in, H2D copy, kernel,
              D2H copy of obs/reward/done/flags every step
   roofline   the step kernel against the measured FP64 FMA-pipe peak (bound "fp64"; the dynamics are
@@ -375,13 +376,15 @@ def run_b200(args):
                    "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"index-range shards x{world}",
                    "l2": "per-step working set 336 B x envs = %.0f MB > 126 MB L2" % (n * 336 / 1e6),
                    "preroll_steps": args.preroll, "mean_rk_attempts": mean_att},
-        "gpu_launches": K,
+        "gpu_launches": K * (2 if env.scratch is not None else 1),
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
                      "frac": ach_tf / peaks["fp64"], "traffic": traffic, "traffic_unit": "B/launch",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_STEP * n,
                      "note": "algorithmic flops/env-step = 985 + 1850 x RK attempts (SURVEY 8d) x envs per launch; "
                              "peak = DFMA micro-benchmark measured in this run (r6_peak_fma)",
-                     "flops_per_env_step": flops_step, "kernel": "step_kernel", "launch_ms": ms_step},
+                     "flops_per_env_step": flops_step,
+                     "kernel": "integrate_kernel + post_kernel (r6_step as two launches)" if env.scratch is not None else "step_kernel",
+                     "launch_ms": ms_step},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gb / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_STEP},

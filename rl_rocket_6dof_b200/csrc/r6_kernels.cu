@@ -231,8 +231,11 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
     b.scratch[n + i] = (uint8_t)natt;
 }
 
+#ifndef R6_POST_BLOCKS
+#define R6_POST_BLOCKS 6         /* resident post-step CTAs per SM (no stage storage: registers are the only limit) */
+#endif
 template <class R>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
 post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
             const float *__restrict__ actions, uint64_t seed)
 {
