@@ -265,6 +265,16 @@ def run_b200(args):
     ms_roll = max_over_ranks(e0.elapsed_time(e1))
     barrier()
 
+    # ---- the same random-action rollout through the integrator | post-step kernel pair (r6_step_random) ----
+    env.step_random(W)
+    barrier()
+    e0.record(stream)
+    env.step_random(K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_rand = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+
     # ---- optional float32 dynamics path (own error bound, tests/test_gpu_fp32.py): same workload ----
     from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
     env32 = Rocket6DOFBatch(n, device=dev, seed=42, env_offset=rank * n, num_envs_global=world * n, precision="fp32",
@@ -391,6 +401,8 @@ def run_b200(args):
         "peaks_measured": {"fp64_tflops": peaks["fp64"], "fp32_tflops": peaks["fp32"]},
         "rollout_fused": {"value": world * n * K / (ms_roll * 1e-3), "unit": UNIT, "ms_per_step": ms_roll / K,
                           "launches": 1, "actions": "in-kernel Philox4x32-10"},
+        "rollout_split": {"value": world * n * K / (ms_rand * 1e-3), "unit": UNIT, "ms_per_step": ms_rand / K,
+                          "launches": 2 * K, "actions": "in-kernel Philox4x32-10 (r6_step_random: integrator | post-step)"},
         "fp32_path": {"value": world * n * K / (ms_f32 * 1e-3), "unit": UNIT, "ms_per_step": ms_f32 / K, "dtype": "f32",
                       "mean_rk_attempts": mean_att32,
                       "roofline": {"bound": "fp32", "achieved": n / (ms_f32 / K * 1e-3) * (F_FIX + F_ATT * mean_att32) / 1e12,

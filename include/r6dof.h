@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 10
+#define R6_ABI_VERSION 11
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -177,6 +177,14 @@ int r6_reset(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offse
  */
 int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset,
             const float *actions, uint64_t seed, void *stream);
+
+/*
+ * r6_step with the synthetic random policy generated in the kernels: action = uniform(-1,1) float32 from Philox
+ * (seed, global env id, step_index) — the same stream as r6_rollout(R6_ACT_PHILOX) with step_base + j = step_index.
+ * Needs R6Buffers.scratch (runs as the integrator | post-step kernel pair).
+ */
+int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, uint64_t seed,
+                   int64_t step_index, void *stream);
 
 /*
  * k fused env-steps per launch with the state held in registers.

@@ -173,6 +173,19 @@ class Rocket6DOFBatch:
         self.steps_done += int(k)
         return traj
 
+    def step_random(self, k: int = 1):
+        """k env-steps with in-kernel Philox actions through the integrator | post-step kernel pair (2k launches).
+        Same action stream and results as `rollout(k)`; faster for large batches, where the two specialised kernels
+        beat the single fused one."""
+        if self.scratch is None:
+            raise RuntimeError("step_random needs split_step=True")
+        with torch.cuda.device(self.device):
+            for _ in range(int(k)):
+                _lib.check(self.lib.r6_step_random(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset,
+                                                   self.seed_value, self.steps_done, self._stream()), self.lib)
+                self.steps_done += 1
+        return self.obs, self.reward, self.done, self.flags
+
     def policy_actions(self, mlp: dict, *, tensor_cores=False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch).
         tensor_cores: False / 0 = float32 FMA network; True / 1 = mma.sync 3xTF32 tiles (faithful to 2e-6);

@@ -211,7 +211,8 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 // that runs at twice the occupancy.  Costs one extra read of the state (+128 B per env-step, HBM is at 10 %).
 template <class R, bool kExact>
 __global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
-integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions)
+integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
+                 uint64_t seed, int64_t step_index)
 {
     const int64_t i = (int64_t)blockIdx.x * kIntThreads + threadIdx.x;
     extern __shared__ double r6_smem[];
@@ -222,7 +223,9 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
     R y[14];
 #pragma unroll
     for (int c = 0; c < 14; c++) y[c] = state[(int64_t)c * n + i];
-    const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+    float a0, a1, a2;
+    if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
+    else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);   // r6_step_random
     int status, natt;
     env_integrate<kExact>(p, b.t_table, y, b.m0[i], b.step_count[i], a0, a1, a2, K, status, natt);
 #pragma unroll
@@ -237,13 +240,15 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
 template <class R>
 __global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
 post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
-            const float *__restrict__ actions, uint64_t seed)
+            const float *__restrict__ actions, uint64_t seed, int64_t step_index)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i < n) {
         EnvT<R> e;
         env_load(b, n, i, e);
-        const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+        float a0, a1, a2;
+        if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
+        else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
         StepOut o;
         env_post(p, dv, e, a0, a1, a2, (int)(int8_t)b.scratch[i], (int)b.scratch[n + i], o);
         if (b.reward) b.reward[i] = o.reward;
@@ -677,15 +682,15 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
 
 template <class R>
 void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset,
-                 const float *actions, uint64_t seed, cudaStream_t s)
+                 const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0)
 {
     const unsigned g = (unsigned)blocks_for(n);
     if (b->scratch != nullptr) {
         const unsigned gi = (unsigned)((n + kIntThreads - 1) / kIntThreads);
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
-        if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions);
-        else integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions);
-        post_kernel<R><<<g, kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed);
+        if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
+        else integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
+        post_kernel<R><<<g, kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index);
         return;
     }
     if (p->dt <= kMaxDtSeries) step_kernel<R, false><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
@@ -757,6 +762,20 @@ int r6_step(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset
     if (p->precision == R6_PREC_F32) launch_step<float>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream);
     else launch_step<double>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream);
     return check_launch("r6_step");
+}
+
+int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, uint64_t seed, int64_t step_index,
+                   void *stream)
+{
+    int rc = validate_step(p, b, n);
+    if (rc) return rc;
+    if (!b->scratch) return fail(R6_EINVAL, "r6_step_random needs R6Buffers.scratch%s");
+    if (n == 0) return R6_OK;
+    if ((rc = ensure_attributes())) return rc;
+    const Derived dv = make_derived(*p);
+    if (p->precision == R6_PREC_F32) launch_step<float>(p, b, dv, n, env_offset, nullptr, seed, (cudaStream_t)stream, step_index);
+    else launch_step<double>(p, b, dv, n, env_offset, nullptr, seed, (cudaStream_t)stream, step_index);
+    return check_launch("r6_step_random");
 }
 
 int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, int32_t k, int32_t mode,

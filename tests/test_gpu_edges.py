@@ -127,3 +127,18 @@ def test_nan_env_does_not_disturb_neighbours():
     torch.cuda.synchronize()
     keep = torch.ones(256, dtype=torch.bool, device="cuda"); keep[100] = False
     assert torch.equal(a.state[:, keep], b.state[:, keep]) and torch.equal(a.reward[keep], b.reward[keep])
+
+
+def test_step_random_equals_fused_rollout():
+    """r6_step_random (integrator | post-step kernels, in-kernel Philox) == r6_rollout(R6_ACT_PHILOX), step by step."""
+    import torch
+    a, b = _mk(3000, seed=12), _mk(3000, seed=12)
+    a.reset(); b.reset()
+    a.step_random(90)
+    b.rollout(90)
+    torch.cuda.synchronize()
+    assert torch.equal(a.episode_id, b.episode_id) and torch.equal(a.step_count, b.step_count)
+    norm = torch.as_tensor(a.params.state_normalizer, device="cuda")[:, None]
+    assert float(((a.state - b.state).abs() / norm).max()) <= 1e-11       # different kernels: FMA contraction may differ
+    sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
+    assert np.array_equal(sa[[0, 2, 3, 4, 5, 6, 7]], sb[[0, 2, 3, 4, 5, 6, 7]]) and a.steps_done == b.steps_done == 90

@@ -13,7 +13,9 @@ def _actions(n, k, seed=0):
 
 
 def test_zero_copy_step_host_equals_staged_copies():
-    """Kernel writing straight into mapped pinned memory == kernel + explicit D2H copies, bit for bit."""
+    """Kernel writing straight into mapped pinned memory == kernels + explicit D2H copies.  The zero-copy path runs
+    the fused step kernel and the staged path the integrator | post-step pair, so the two agree to float64
+    round-off (different FMA contraction), with identical episode boundaries."""
     import torch
     from rl_rocket_6dof_b200 import make_vec_env
     n, k = 4096, 220
@@ -27,11 +29,14 @@ def test_zero_copy_step_host_equals_staged_copies():
     for j in range(k):
         ra = a.step_host(pinned[j])              # pinned input: no staging copy at all
         rb = b.step_host(acts[j])                # numpy input: staged through the pinned buffer
-        for x, y in zip(ra, rb):
-            assert np.array_equal(x, y), j
+        assert np.array_equal(ra[2], rb[2]), j                              # dones
+        assert f32_ulp_diff(ra[0], rb[0]).max() <= 1.0, j                   # float32 observations
+        assert np.abs(ra[1] - rb[1]).max() <= 1e-5, j                       # float32 rewards
         n_done += int(ra[2].sum())
     assert n_done > n // 2                       # episodes ended and were auto-reset on both paths
-    assert torch.equal(a.batch.state, b.batch.state) and torch.equal(a.batch.episode_id, b.batch.episode_id)
+    norm = torch.as_tensor(a.batch.params.state_normalizer, device="cuda")[:, None]
+    assert float(((a.batch.state - b.batch.state).abs() / norm).max()) <= 1e-11
+    assert torch.equal(a.batch.episode_id, b.batch.episode_id) and torch.equal(a.batch.step_count, b.batch.step_count)
     assert a.h2d_bytes_per_step == n * 12 and a.d2h_bytes_per_step == n * (13 * 4 + 4 + 2)
 
 
