@@ -883,8 +883,11 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
         }
     }
     hi = hi_s;
-    double x = from_right ? hi_s : lo;
-    double fx = from_right ? fhi_s : flo;
+    // start from the upper end in both cases: in the convex case Newton is monotone from there; in the concave case
+    // (root left of the inflection point) its first step overshoots to the left of the root and is monotone after
+    // that, whereas starting at lo = 0 with f'(0) = c3 <= 0 would fall back to bisection for many iterations
+    double x = hi_s;
+    double fx = fhi_s;
     for (int it = 0; it < 100; it++) {
         const double dfx = quartic_df(c0, c2, c3, x);
         double xn = x - fx * fast_rcp(dfx);
