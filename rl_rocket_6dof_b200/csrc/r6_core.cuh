@@ -860,6 +860,7 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
         return NAN;
     }
     double hi_s = hi, fhi_s = fhi;
+    bool certified = false;      // bracket inside the convex region AND tightened to ~1e-5 by the float32 walk
     if (from_right) {
         // The far end of the bracket is the Fujiwara bound, from which Newton on a quartic first creeps in
         // by factors of 3/4.  Walk that stretch in float32 (FP32 pipe, no safeguards needed: the result is
@@ -879,7 +880,7 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
         const double xs = (double)xf * (1.0 + 1e-5);
         if (xs > lo && xs < hi) {
             const double fs = quartic_f(c0, c2, c3, c4, xs);
-            if (fs > 0) { hi_s = xs; fhi_s = fs; }
+            if (fs > 0) { hi_s = xs; fhi_s = fs; certified = !(ti >= B); }
         }
     }
     hi = hi_s;
@@ -888,7 +889,20 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
     // that, whereas starting at lo = 0 with f'(0) = c3 <= 0 would fall back to bisection for many iterations
     double x = hi_s;
     double fx = fhi_s;
-    for (int it = 0; it < 100; it++) {
+    if (certified) {
+        // f is convex on [lo, hi] with f(lo) <= 0 < f(hi) and hi within ~1e-5 of the root: plain Newton from hi is
+        // monotone, cannot leave the bracket and converges quadratically (1e-5 -> 1e-10 -> 1e-20): three bare steps,
+        // no bracket bookkeeping.  If the third step still moved, fall through to the safeguarded loop.
+        double dx = 0;
+#pragma unroll
+        for (int it = 0; it < 3; it++) {
+            dx = fx * fast_rcp(quartic_df(c0, c2, c3, x));
+            x -= dx;
+            fx = quartic_f(c0, c2, c3, c4, x);
+        }
+        if (!(fabs(dx) <= 1e-11 * fabs(x))) { certified = false; x = hi_s; fx = fhi_s; }
+    }
+    for (int it = 0; it < 100 && !certified; it++) {
         const double dfx = quartic_df(c0, c2, c3, x);
         double xn = x - fx * fast_rcp(dfx);
         if (fabs(xn - x) <= 4.440892098500626e-16 * fabs(x)) break;   // converged (monotone Newton stalls at the root)

@@ -78,3 +78,31 @@ def run_montecarlo(n_episodes: int, weights: Dict[str, np.ndarray], env_config: 
 def format_report(res: dict) -> str:
     """The lines montecarlo_script.py:74-81 prints."""
     return "\n".join(f"The {h} has mean:{res['mean'][h]} and standard deviation: {res['std'][h]}" for h in HEADER)
+
+
+def main(argv=None) -> int:
+    """`python -m rl_rocket_6dof_b200.montecarlo --policy best_model_2bo71j9m.zip` — what `python montecarlo_script.py`
+    does in the reference (results_montecarlo.csv + the mean / std lines), for any number of episodes."""
+    import argparse
+
+    from .params import load_config
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--policy", required=True, help="SB3 model archive (.zip) or .npz with mlp_w0 .. mlp_b2")
+    ap.add_argument("--episodes", type=int, default=30)
+    ap.add_argument("--config", default=None, help="config.yaml (default: the packaged reference configuration)")
+    ap.add_argument("--csv", default="results_montecarlo.csv")
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--tensor-cores", action="store_true", help="evaluate the policy with the 3xTF32 MMA tiles")
+    a = ap.parse_args(argv)
+    w = _policy.load_npz(a.policy) if a.policy.endswith(".npz") else _policy.load_sb3_zip(a.policy)
+    sb3_config, env_config = load_config(a.config)
+    res = run_montecarlo(a.episodes, w, env_config, sb3_config, device=a.device, seed=a.seed, csv_path=a.csv,
+                         tensor_cores=a.tensor_cores)
+    print(format_report(res))
+    print(f"episodes: {a.episodes}, landed: {int(res['landed'].sum())}, mean length {res['episode_length'].mean():.1f} steps")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

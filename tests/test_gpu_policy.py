@@ -203,6 +203,15 @@ def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path, tensor_core
     assert res["stats"]["episodes"] == n
 
 
+def test_montecarlo_cli(tmp_path, capsys):
+    from rl_rocket_6dof_b200 import montecarlo
+    out = str(tmp_path / "mc.csv")
+    assert montecarlo.main(["--policy", GOLD, "--episodes", "64", "--csv", out, "--device", "cuda:0", "--seed", "3"]) == 0
+    text = capsys.readouterr().out
+    assert "The final_position_error has mean:" in text and "episodes: 64" in text
+    assert len(open(out).read().strip().splitlines()) == 65
+
+
 def test_one_episode_rollout_freezes_finished_envs():
     import torch
     from rl_rocket_6dof_b200.batch import ACT_PHILOX, Rocket6DOFBatch
