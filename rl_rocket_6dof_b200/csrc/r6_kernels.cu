@@ -687,7 +687,7 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
 {
     const unsigned g = (unsigned)blocks_for(n);
     // two launches only pay off once the grid fills the machine several times over
-    if (b->scratch != nullptr && n > kSplitMinEnvs) {
+    if (b->scratch != nullptr && (n > kSplitMinEnvs || actions == nullptr)) {      // r6_step_random always splits
         const unsigned gi = (unsigned)((n + kIntThreads - 1) / kIntThreads);
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
         if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
