@@ -22,6 +22,7 @@ ACT_PHILOX, ACT_MLP, ACT_BUFFER, ACT_MLP_TC = 0, 1, 2, 3
 F_EVENT, F_OOB, F_TRUNCATED = 0x01, 0x02, 0x04
 F_LANDING_ALL = 0xF8
 FLAG_NAMES = ["zero_height", "velocity_limit", "landing_radius", "attitude_limit", "omega_limit"]
+SPLIT_MIN_ENVS = 65536
 STAT_NAMES = ["episodes", "return_sum", "length_sum", "landed", "ground", "out_of_bounds", "truncated", "steps"]
 
 
@@ -77,9 +78,11 @@ class Rocket6DOFBatch:
             self.terminal_state = torch.zeros(14, n, dtype=sdt, device=dev)
             self.ep_info = torch.zeros(2, n, dtype=f32, device=dev)
             self.stats = torch.zeros(8, dtype=f64, device=dev)
+            # r6_step as two kernels (integrator | post-step) needs 2 bytes of device scratch per env; two launches
+            # only pay off once the grid fills the machine several times over (measured cross-over: 2^16..2^17 envs)
             if split_step is None:
-                split_step = os.environ.get("R6_SPLIT_STEP", "1") != "0"
-            # r6_step as two kernels (integrator | post-step) needs 2 bytes of device scratch per env
+                env_flag = os.environ.get("R6_SPLIT_STEP")
+                split_step = (n > SPLIT_MIN_ENVS) if env_flag is None else (env_flag != "0")
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
             self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
@@ -177,8 +180,9 @@ class Rocket6DOFBatch:
         """k env-steps with in-kernel Philox actions through the integrator | post-step kernel pair (2k launches).
         Same action stream and results as `rollout(k)`; faster for large batches, where the two specialised kernels
         beat the single fused one."""
-        if self.scratch is None:
-            raise RuntimeError("step_random needs split_step=True")
+        if self.scratch is None:                       # the random-action step exists only as the kernel pair
+            self.scratch = torch.zeros(2, self.num_envs, dtype=torch.uint8, device=self.device)
+            self._b.scratch = self.scratch.data_ptr()
         with torch.cuda.device(self.device):
             for _ in range(int(k)):
                 _lib.check(self.lib.r6_step_random(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset,

@@ -52,7 +52,6 @@ template <class R> constexpr int min_blocks() { return sizeof(R) == 4 ? R6_MIN_B
 #define R6_INT_THREADS 32
 #endif
 constexpr int kIntThreads = R6_INT_THREADS;
-constexpr int64_t kSplitMinEnvs = 65536;     // below this r6_step uses the single fused kernel (one launch latency)
 #ifndef R6_INT_CTAS_F64
 #define R6_INT_CTAS_F64 (R6_MIN_BLOCKS * R6_THREADS / R6_INT_THREADS)      /* resident integrator CTAs per SM, float64 */
 #endif
@@ -686,8 +685,7 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
                  const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0)
 {
     const unsigned g = (unsigned)blocks_for(n);
-    // two launches only pay off once the grid fills the machine several times over
-    if (b->scratch != nullptr && (n > kSplitMinEnvs || actions == nullptr)) {      // r6_step_random always splits
+    if (b->scratch != nullptr) {
         const unsigned gi = (unsigned)((n + kIntThreads - 1) / kIntThreads);
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
         if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
