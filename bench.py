@@ -256,10 +256,10 @@ def run_b200(args):
     sd = env.stats_dict(stats)
 
     # ---- fused rollout kernel (k steps per launch, in-kernel Philox actions) -----------------
-    env.rollout(K)
+    env.rollout(K, fused=True)
     barrier()
     e0.record(stream)
-    env.rollout(K)
+    env.rollout(K, fused=True)
     e1.record(stream)
     torch.cuda.synchronize()
     ms_roll = max_over_ranks(e0.elapsed_time(e1))

@@ -146,8 +146,18 @@ class Rocket6DOFBatch:
         return self.obs, self.reward, self.done, self.flags
 
     def rollout(self, k: int, mode: int = ACT_PHILOX, *, actions: Optional[torch.Tensor] = None,
-                mlp: Optional[dict] = None, record: bool = False):
-        """k fused env-steps in one launch (state stays in registers, auto-reset on)."""
+                mlp: Optional[dict] = None, record: bool = False, fused: Optional[bool] = None):
+        """k env-steps without a host round trip.  fused=True: one launch, state in registers for all k steps
+        (`r6_rollout`).  For the random policy on large auto-reset batches the integrator | post-step kernel pair
+        is faster than the fused kernel, so fused=None picks `step_random` there (same action stream, results equal to
+        round-off); recording, other action sources and one-episode semantics always use the fused kernel."""
+        if fused is None:
+            fused = not (mode == ACT_PHILOX and not record and self.auto_reset and self.num_envs > SPLIT_MIN_ENVS)
+        if not fused:
+            if mode != ACT_PHILOX or record:
+                raise ValueError("the split rollout exists for the random policy without recording")
+            self.step_random(k)
+            return None
         n = self.num_envs
         traj = None
         po = pa = pr = pd = 0
