@@ -347,22 +347,40 @@ R6_HD void density_setup(StepConstT<R> &c, R h0)
 // kExact = false: binomial series of (1 - d)^p around the step's initial height, d = kd (h - h0),
 // p = -kRhoExp, to d^6; the next term is 2.6e-3 d^7, i.e. < 3e-17 for |d| <= 0.01 (|h - h0| <= 400 m).
 // The launcher picks kExact = true when dt is so large that this cannot be guaranteed (dt > 0.25 s).
+// series coefficients b_1..b_6 of (1 - d)^p.  On the device they live in the constant bank so that each Horner
+// step is ONE DFMA with a c[bank][offset] operand; as literals ptxas materialises every 64-bit immediate with two
+// UMOVs, which doubled the instruction count of this function (it runs in every right-hand-side evaluation).
+struct RhoStep { double b[7]; float bf[7]; };
+constexpr RhoStep make_rho_step()
+{
+    constexpr double p = -kRhoExp;
+    RhoStep r{};
+    r.b[0] = 1.0;
+    for (int k = 0; k < 6; k++) r.b[k + 1] = r.b[k] * (-(p - k)) / (k + 1);
+    for (int k = 0; k < 7; k++) r.bf[k] = (float)r.b[k];
+    return r;
+}
+constexpr RhoStep kRhoStepHost = make_rho_step();
+#if defined(__CUDACC__)
+__constant__ RhoStep kRhoStepDev = make_rho_step();
+#endif
+#if defined(__CUDA_ARCH__)
+#define R6_RHO_STEP ::r6::kRhoStepDev
+#else
+#define R6_RHO_STEP ::r6::kRhoStepHost
+#endif
+R6_HD double rho_b(int k, double) { return R6_RHO_STEP.b[k]; }
+R6_HD float rho_b(int k, float) { return R6_RHO_STEP.bf[k]; }
+
 template <bool kExact, class R>
 R6_HD R density(const StepConstT<R> &c, R h)
 {
     if (kExact) return density_exact(h);
     const R d = c.kd * (h - c.h0);
-    constexpr double p = -kRhoExp;
-    constexpr R b1 = R(-p);
-    constexpr R b2 = R(p * (p - 1) / 2);
-    constexpr R b3 = R(-p * (p - 1) * (p - 2) / 6);
-    constexpr R b4 = R(p * (p - 1) * (p - 2) * (p - 3) / 24);
-    constexpr R b5 = R(-p * (p - 1) * (p - 2) * (p - 3) * (p - 4) / 120);
-    constexpr R b6 = R(p * (p - 1) * (p - 2) * (p - 3) * (p - 4) * (p - 5) / 720);
     // float: d^4 and beyond are below the rounding of the sum (|d| <= 0.01)
-    R s = (sizeof(R) == 8) ? fma(fma(fma(b6, d, b5), d, b4), d, b3) : b3;
-    s = fma(s, d, b2);
-    s = fma(s, d, b1);
+    R s = (sizeof(R) == 8) ? fma(fma(fma(rho_b(6, R()), d, rho_b(5, R())), d, rho_b(4, R())), d, rho_b(3, R())) : rho_b(3, R());
+    s = fma(s, d, rho_b(2, R()));
+    s = fma(s, d, rho_b(1, R()));
     s = fma(s, d, R(1.0));
     return c.rho0 * s;
 }
