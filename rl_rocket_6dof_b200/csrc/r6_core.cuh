@@ -828,58 +828,61 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
 //   * else f has a local minimum at s2 > t_i (found by monotone Newton on the convex f'); the largest
 //     root is right of s2 if f(s2) <= 0, otherwise it is the single root left of t_i.
 // Every Newton step is safeguarded by the bracket (falls back to bisection), so it terminates.
-R6_HD double quartic_f(double c0, double c2, double c3, double c4, double t)
+template <class W>
+R6_HD W quartic_f(W c0, W c2, W c3, W c4, W t)
 {
-    double t2 = t * t;
+    W t2 = t * t;
     return fma(fma(c0, t2, c2), t2, fma(c3, t, c4));
 }
-R6_HD double quartic_df(double c0, double c2, double c3, double t)
+template <class W>
+R6_HD W quartic_df(W c0, W c2, W c3, W t)
 {
     return fma(fma(4 * c0, t * t, 2 * c2), t, c3);
 }
-R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
+template <class W>
+R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4)
 {
-    if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return NAN;       // no sign change => no positive root
+    if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return W(NAN);       // no sign change => no positive root
     // Fujiwara bound on the root moduli; float32 is plenty for a bound (inflated by 1e-4)
-    const double ic0 = fast_rcp(c0);
+    const W ic0 = fast_rcp(c0);
     const float a2 = (float)(fabs(c2) * ic0), a1 = (float)(fabs(c3) * ic0), a0 = (float)(fabs(c4) * ic0);
-    const double B = (double)(2.0002f * fmaxf(sqrtf(a2), fmaxf(cbrtf(a1), sqrtf(sqrtf(0.5f * a0)))));
-    if (!(B > 0) || !isfinite(B)) return NAN;
-    double lo = 0, hi = B;
+    const W B = (W)(2.0002f * fmaxf(sqrtf(a2), fmaxf(cbrtf(a1), sqrtf(sqrtf(0.5f * a0)))));
+    if (!(B > 0) || !isfinite(B)) return W(NAN);
+    W lo = 0, hi = B;
     bool from_right = true;
-    const double ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * (1.0 / 6)) : 0.0;
+    const W ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * W(1.0 / 6)) : W(0.0);
     if (ti > 0 && ti < B) {
-        const double fi = quartic_f(c0, c2, c3, c4, ti);
+        const W fi = quartic_f(c0, c2, c3, c4, ti);
         if (fi <= 0) { lo = ti; }
         else {
-            const double gi = quartic_df(c0, c2, c3, ti);
+            const W gi = quartic_df(c0, c2, c3, ti);
             if (gi >= 0) { hi = ti; from_right = false; }
             else {
                 // local minimum s2 > ti: monotone Newton on f' (convex on t > 0) from the right
-                double s = B;
+                W s = B;
                 for (int it = 0; it < 60; it++) {
-                    const double d1 = quartic_df(c0, c2, c3, s);
-                    const double d2 = fma(12 * c0, s * s, 2 * c2);
+                    const W d1 = quartic_df(c0, c2, c3, s);
+                    const W d2 = fma(12 * c0, s * s, 2 * c2);
                     if (!(d2 > 0)) break;
-                    const double sn = s - d1 * fast_rcp(d2);
+                    const W sn = s - d1 * fast_rcp(d2);
                     if (!(sn < s) || sn <= ti) { break; }
                     s = sn;
                 }
-                const double fs = quartic_f(c0, c2, c3, c4, s);
+                const W fs = quartic_f(c0, c2, c3, c4, s);
                 if (fs <= 0) { lo = s; }
                 else { hi = ti; from_right = false; }   // f > 0 on [ti, inf): the root is left of ti
             }
         }
     }
-    const double flo = quartic_f(c0, c2, c3, c4, lo), fhi = quartic_f(c0, c2, c3, c4, hi);
+    const W flo = quartic_f(c0, c2, c3, c4, lo), fhi = quartic_f(c0, c2, c3, c4, hi);
     if (flo == 0 && lo > 0) return lo;
     if (!(flo < 0) || !(fhi > 0)) {
         if (fhi == 0) return hi;
-        return NAN;
+        return W(NAN);
     }
-    double hi_s = hi, fhi_s = fhi;
+    W hi_s = hi, fhi_s = fhi;
     bool certified = false;      // bracket inside the convex region AND tightened to ~1e-5 by the float32 walk
-    if (from_right) {
+    if (from_right && sizeof(W) == 8) {
         // The far end of the bracket is the Fujiwara bound, from which Newton on a quartic first creeps in
         // by factors of 3/4.  Walk that stretch in float32 (FP32 pipe, no safeguards needed: the result is
         // only a PROPOSAL for a tighter upper end, accepted if float64 confirms lo < x < hi and f(x) > 0).
@@ -895,9 +898,9 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
             if (!(xf - xn > 2e-6f * xf)) break;
             xf = xn;
         }
-        const double xs = (double)xf * (1.0 + 1e-5);
+        const W xs = (W)xf * W(1.0 + 1e-5);
         if (xs > lo && xs < hi) {
-            const double fs = quartic_f(c0, c2, c3, c4, xs);
+            const W fs = quartic_f(c0, c2, c3, c4, xs);
             if (fs > 0) { hi_s = xs; fhi_s = fs; certified = !(ti >= B); }
         }
     }
@@ -905,37 +908,37 @@ R6_HD double tgo_largest_root(double c0, double c2, double c3, double c4)
     // start from the upper end in both cases: in the convex case Newton is monotone from there; in the concave case
     // (root left of the inflection point) its first step overshoots to the left of the root and is monotone after
     // that, whereas starting at lo = 0 with f'(0) = c3 <= 0 would fall back to bisection for many iterations
-    double x = hi_s;
-    double fx = fhi_s;
+    W x = hi_s;
+    W fx = fhi_s;
     if (certified) {
         // f is convex on [lo, hi] with f(lo) <= 0 < f(hi) and hi within ~1e-5 of the root: plain Newton from hi is
         // monotone, cannot leave the bracket and converges quadratically (1e-5 -> 1e-10 -> 1e-20): three bare steps,
         // no bracket bookkeeping.  If the third step still moved, fall through to the safeguarded loop.
-        double dx = 0;
+        W dx = 0;
 #pragma unroll
         for (int it = 0; it < 3; it++) {
             dx = fx * fast_rcp(quartic_df(c0, c2, c3, x));
             x -= dx;
             fx = quartic_f(c0, c2, c3, c4, x);
         }
-        if (!(fabs(dx) <= 1e-11 * fabs(x))) { certified = false; x = hi_s; fx = fhi_s; }
+        if (!(fabs(dx) <= W(1e-11) * fabs(x))) { certified = false; x = hi_s; fx = fhi_s; }
     }
     for (int it = 0; it < 100 && !certified; it++) {
-        const double dfx = quartic_df(c0, c2, c3, x);
-        double xn = x - fx * fast_rcp(dfx);
-        if (fabs(xn - x) <= 4.440892098500626e-16 * fabs(x)) break;   // converged (monotone Newton stalls at the root)
-        if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);        // safeguard: bisection
-        const double fn_ = quartic_f(c0, c2, c3, c4, xn);
+        const W dfx = quartic_df(c0, c2, c3, x);
+        W xn = x - fx * fast_rcp(dfx);
+        if (fabs(xn - x) <= 2 * Real<W>::eps * fabs(x)) break;   // converged (monotone Newton stalls at the root)
+        if (!(xn >= lo && xn <= hi)) xn = W(0.5) * (lo + hi);        // safeguard: bisection
+        const W fn_ = quartic_f(c0, c2, c3, c4, xn);
         x = xn; fx = fn_;
         if (fn_ > 0) hi = xn; else if (fn_ < 0) lo = xn; else break;
-        if (hi - lo <= 2.220446049250313e-16 * hi) break;
+        if (hi - lo <= Real<W>::eps * hi) break;
     }
     // final polish: one unconditional Newton step with a true division (converged iterates barely move)
     {
-        const double dfx = quartic_df(c0, c2, c3, x);
+        const W dfx = quartic_df(c0, c2, c3, x);
         if (dfx != 0) {
-            const double xn = x - quartic_f(c0, c2, c3, c4, x) / dfx;
-            if (xn > 0 && fabs(xn - x) <= 1e-9 * x) x = xn;
+            const W xn = x - quartic_f(c0, c2, c3, c4, x) / dfx;
+            if (xn > 0 && fabs(xn - x) <= W(sizeof(W) == 8 ? 1e-9 : 1e-4) * x) x = xn;
         }
     }
     return x;
@@ -1000,34 +1003,35 @@ R6_HD float obs_component(const R6Params &, const Derived &dv, const float *y, i
 // 1052-1111), reduced to what the env needs: the two limit tests.  With a = w-y, b = z-x, c = y+w,
 // d = -x-z:  cos(e0) = (ac+bd)/(|ab||cd|), sin(e1) = (|cd|^2-|ab|^2)/(|ab|^2+|cd|^2),
 // cos(e2) = (ac-bd)/(|ab||cd|); gimbal lock (|e1 +- pi/2| <= 1e-7): e0 = 2 hs or -2 hd, e2 = 0.
-R6_HD void euler_limit_tests(const AngleTests &at, double w, double x, double y, double z, bool &violated,
+template <class W>
+R6_HD void euler_limit_tests(const AngleTests &at, W w, W x, W y, W z, bool &violated,
                              bool &land_ok)
 {
-    const double a = w - y, b = z - x, c = y + w, d = -x - z;
-    const double Q2 = a * a + b * b, P2 = c * c + d * d;
-    constexpr double tan2_lock = 2.5e-15;     // tan(5e-8)^2
+    const W a = w - y, b = z - x, c = y + w, d = -x - z;
+    const W Q2 = a * a + b * b, P2 = c * c + d * d;
+    constexpr W tan2_lock = W(2.5e-15);     // tan(5e-8)^2
     const bool case1 = P2 <= tan2_lock * Q2;
     const bool case2 = Q2 <= tan2_lock * P2;
-    double cos0, cos2;
+    W cos0, cos2;
     if (!(case1 || case2)) {
-        const double inv = fast_rcp(fast_sqrt(Q2 * P2));
+        const W inv = fast_rcp(fast_sqrt(Q2 * P2));
         cos0 = (a * c + b * d) * inv;
         cos2 = (a * c - b * d) * inv;
     } else if (case1) {
-        cos0 = (a * a - b * b) / Q2; cos2 = 1.0;
+        cos0 = (a * a - b * b) / Q2; cos2 = W(1.0);
     } else {
-        cos0 = (c * c - d * d) / P2; cos2 = 1.0;
+        cos0 = (c * c - d * d) / P2; cos2 = W(1.0);
     }
-    const double sin1 = (P2 - Q2) / (P2 + Q2);
-    const double m[3] = {cos0, fabs(sin1), cos2};
+    const W sin1 = (P2 - Q2) / (P2 + Q2);
+    const W m[3] = {cos0, fabs(sin1), cos2};
     violated = false;
     land_ok = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         // |e| > L  <=>  cos e < cos L  (i = 0, 2)   |  |sin e1| > sin L (i = 1)
-        bool v = (i == 1) ? (m[i] > at.viol_thr[i]) : (m[i] < at.viol_thr[i]);
+        bool v = (i == 1) ? (m[i] > (W)at.viol_thr[i]) : (m[i] < (W)at.viol_thr[i]);
         v = (at.viol_mode[i] == 1) ? v : (at.viol_mode[i] == 2);
-        bool l = (i == 1) ? (m[i] < at.land_thr[i]) : (m[i] > at.land_thr[i]);
+        bool l = (i == 1) ? (m[i] < (W)at.land_thr[i]) : (m[i] > (W)at.land_thr[i]);
         l = (at.land_mode[i] == 1) ? l : (at.land_mode[i] == 2);
         violated = violated || v;
         land_ok = land_ok || l;
@@ -1052,63 +1056,70 @@ struct PostOut {
 
 // rocket_env.py:206-231 after the simulator step.  S = post-step state with the quaternion already
 // re-normalised in float64 (simulator.py:97).
-template <class RS>
-R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<RS> &cr, const double *S, float u2,
+// W = working precision of the float64 parts of the reference's reward (t_go root, a_targ, thrust rotation, Euler
+// tests): double on the parity path (S = the float64 state), float on the float32 path (S = the float32 state; the
+// reward then carries float32 round-off, inside that path's own bound).
+R6_HD float to_f32(double x) { return f64_to_f32(x); }
+R6_HD float to_f32(float x) { return x; }
+R6_HD double w_exp(double x) { return exp(x); }
+R6_HD float w_exp(float x) { return expf(x); }
+template <class RS, class W>
+R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<RS> &cr, const W *S, float u2,
                      float v0_episode, int status, PostOut &o)
 {
-    struct { double Tb0, Tb1, Tb2; } c = {(double)cr.Tb0, (double)cr.Tb1, (double)cr.Tb2};
+    struct { W Tb0, Tb1, Tb2; } c = {(W)cr.Tb0, (W)cr.Tb1, (W)cr.Tb2};
     float s[14];
 #pragma unroll
-    for (int i = 0; i < 14; i++) s[i] = f64_to_f32(S[i]);                      // :206
+    for (int i = 0; i < 14; i++) s[i] = to_f32(S[i]);                          // :206
     const float m = s[13];
     const bool oob = !(s[0] >= p.bounds_low[0] && s[0] <= p.bounds_high[0] && s[1] >= p.bounds_low[1] &&
                        s[1] <= p.bounds_high[1] && s[2] >= p.bounds_low[2] && s[2] <= p.bounds_high[2]);   // :591-593
     const float vn = f32_sqrt(sdot3(s[3], s[4], s[5], s[3], s[4], s[5]));
     const float rn = f32_sqrt(sdot3(s[0], s[1], s[2], s[0], s[1], s[2]));
     bool att_viol, att_land;
-    euler_limit_tests(at, (double)s[6], (double)s[7], (double)s[8], (double)s[9], att_viol, att_land);
-    double shaping;
+    euler_limit_tests(at, (W)s[6], (W)s[7], (W)s[8], (W)s[9], att_viol, att_land);
+    W shaping;
     o.tgo_missing = false;
     if (!p.shaping_velocity) {
         // _compute_atarg (:526-566)
-        const double c0 = (-9.81) * (-9.81);
+        const W c0 = W((-9.81) * (-9.81));
         const float c2 = f32_mul(-4.0f, f32_mul(vn, vn));
         const float c3 = f32_mul(-24.0f, sdot3(s[0], s[1], s[2], s[3], s[4], s[5]));
         const float c4 = f32_mul(-36.0f, f32_mul(rn, rn));
-        const double tgo = tgo_largest_root(c0, (double)c2, (double)c3, (double)c4);
+        const W tgo = tgo_largest_root(c0, (W)c2, (W)c3, (W)c4);
         o.tgo_missing = !(tgo > 0);
-        const double itg = fast_rcp(tgo), itg2 = itg * itg;
-        const double q0 = (double)f32_mul(-6.0f, s[0]) * itg2 - (double)f32_mul(4.0f, s[3]) * itg + 9.81;
-        const double q1 = (double)f32_mul(-6.0f, s[1]) * itg2 - (double)f32_mul(4.0f, s[4]) * itg;
-        const double q2 = (double)f32_mul(-6.0f, s[2]) * itg2 - (double)f32_mul(4.0f, s[5]) * itg;
-        const double U = (double)f32_div(p.max_thrust, m);
-        const double qn = fast_sqrt(q0 * q0 + q1 * q1 + q2 * q2);
-        const double k = (qn <= U) ? 1.0 : U * fast_rcp(qn);
+        const W itg = fast_rcp(tgo), itg2 = itg * itg;
+        const W q0 = (W)f32_mul(-6.0f, s[0]) * itg2 - (W)f32_mul(4.0f, s[3]) * itg + W(9.81);
+        const W q1 = (W)f32_mul(-6.0f, s[1]) * itg2 - (W)f32_mul(4.0f, s[4]) * itg;
+        const W q2 = (W)f32_mul(-6.0f, s[2]) * itg2 - (W)f32_mul(4.0f, s[5]) * itg;
+        const W U = (W)f32_div(p.max_thrust, m);
+        const W qn = fast_sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const W k = (qn <= U) ? W(1.0) : U * fast_rcp(qn);
         // thrust acceleration from the float64 post-step quaternion (:339-340, simulator.py:177-186)
-        RotU R = rot_unnormalised(S[6], S[7], S[8], S[9]);
-        const double im = fast_rcp(R.n2 * (double)m);
-        const double d0 = (R.m00 * c.Tb0 + R.m01 * c.Tb1 + R.m02 * c.Tb2) * im - q0 * k;
-        const double d1 = (R.m10 * c.Tb0 + R.m11 * c.Tb1 + R.m12 * c.Tb2) * im - q1 * k;
-        const double d2 = (R.m20 * c.Tb0 + R.m21 * c.Tb1 + R.m22 * c.Tb2) * im - q2 * k;
-        shaping = p.alfa * fast_sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        RotUT<W> R = rot_unnormalised(S[6], S[7], S[8], S[9]);
+        const W im = fast_rcp(R.n2 * (W)m);
+        const W d0 = (R.m00 * c.Tb0 + R.m01 * c.Tb1 + R.m02 * c.Tb2) * im - q0 * k;
+        const W d1 = (R.m10 * c.Tb0 + R.m11 * c.Tb1 + R.m12 * c.Tb2) * im - q1 * k;
+        const W d2 = (R.m20 * c.Tb0 + R.m21 * c.Tb1 + R.m22 * c.Tb2) * im - q2 * k;
+        shaping = (W)p.alfa * fast_sqrt(d0 * d0 + d1 * d1 + d2 * d2);
     } else {
         // _compute_vtarg (:646-674) + :349
-        double rh0, rh1, rh2, vh0, tau;
-        if ((double)s[0] > p.waypoint) {
-            rh0 = (double)s[0] - p.waypoint; rh1 = s[1]; rh2 = s[2];
-            vh0 = (double)s[3] + 2.0; tau = 20;
+        W rh0, rh1, rh2, vh0, tau;
+        if ((W)s[0] > (W)p.waypoint) {
+            rh0 = (W)s[0] - (W)p.waypoint; rh1 = s[1]; rh2 = s[2];
+            vh0 = (W)s[3] + W(2.0); tau = 20;
         } else {
-            rh0 = (double)f32_add(s[0], 1.0f); rh1 = 0; rh2 = 0;
-            vh0 = (double)s[3] + 1.0; tau = 100;
+            rh0 = (W)f32_add(s[0], 1.0f); rh1 = 0; rh2 = 0;
+            vh0 = (W)s[3] + W(1.0); tau = 100;
         }
-        const double rh = sqrt(rh0 * rh0 + rh1 * rh1 + rh2 * rh2);
-        const double vh = sqrt(vh0 * vh0 + (double)s[4] * (double)s[4] + (double)s[5] * (double)s[5]);
-        const double tg = rh / vh, kk = 1 - exp(-tg / tau), den = fmax(1e-3, rh);
-        const double mv0 = (double)(-v0_episode);
-        const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * kk;
-        const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * kk;
-        const double d2 = (double)s[5] - (mv0 * (rh2 / den)) * kk;
-        shaping = p.alfa * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        const W rh = sqrt(rh0 * rh0 + rh1 * rh1 + rh2 * rh2);
+        const W vh = sqrt(vh0 * vh0 + (W)s[4] * (W)s[4] + (W)s[5] * (W)s[5]);
+        const W tg = rh / vh, kk = 1 - w_exp(-tg / tau), den = fmax(W(1e-3), rh);
+        const W mv0 = (W)(-v0_episode);
+        const W d0 = (W)s[3] - (mv0 * (rh0 / den)) * kk;
+        const W d1 = (W)s[4] - (mv0 * (rh1 / den)) * kk;
+        const W d2 = (W)s[5] - (mv0 * (rh2 / den)) * kk;
+        shaping = (W)p.alfa * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
     }
     const float pen = f32_mul(p.beta, u2);                                     // :355
     const double att = att_viol ? p.gamma : 0.0;                               // :366-369
@@ -1125,11 +1136,11 @@ R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<R
     const float dv = f32_sub(p.max_v_f, vn);
     const double final_vel = (rn < p.max_r_f && f_zero) ? (dv > 0 ? (double)f32_mul(dv, p.w_v_f) : 0.0) : 0.0;   // :401
     double reward = 0;
-    reward += shaping; reward += (double)pen; reward += p.eta; reward += att; reward += goal;
+    reward += (double)shaping; reward += (double)pen; reward += p.eta; reward += att; reward += goal;
     reward += final_pos; reward += final_vel;                                  // :362
     if (oob) reward += p.oob_penalty;                                          // :228-229
     o.reward = reward;
-    o.terms[0] = shaping; o.terms[1] = (double)pen; o.terms[2] = p.eta; o.terms[3] = att;
+    o.terms[0] = (double)shaping; o.terms[1] = (double)pen; o.terms[2] = p.eta; o.terms[3] = att;
     o.terms[4] = goal; o.terms[5] = final_pos; o.terms[6] = final_vel;
     uint32_t fl = 0;
     if (status != 0) fl |= R6_F_EVENT;
@@ -1376,14 +1387,7 @@ R6_HD void env_post(const R6Params &p, const Derived &dv, EnvT<R> &e, float a0, 
     o.status = status;
     o.natt = natt;
     e.k += 1;
-    if constexpr (sizeof(R) == 8) {
-        post_step(p, dv.at, c, reinterpret_cast<const double *>(e.y), u2, e.v0, o.status, o.post);
-    } else {
-        double S[14];
-#pragma unroll
-        for (int i = 0; i < 14; i++) S[i] = (double)e.y[i];
-        post_step(p, dv.at, c, S, u2, e.v0, o.status, o.post);
-    }
+    post_step(p, dv.at, c, e.y, u2, e.v0, o.status, o.post);      // working precision = R
     uint32_t fl = o.post.flags;
     const bool done = (fl & (R6_F_EVENT | R6_F_OOB)) != 0;                    // rocket_env.py:213
     const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit
