@@ -1,10 +1,16 @@
 // r6_kernels.cu — sm_100a kernels + the C ABI of include/r6dof.h.
 //
-// One thread owns one environment: its 14 float64 state components are loaded from the
-// component-major (SoA) state array with fully coalesced 8-byte accesses (a warp reads 256
-// contiguous bytes per component), stay in registers through the whole adaptive RK45 step, the
-// reward / termination logic and the auto-reset, and are written back the same way.  There is no
-// tensor-core work here (the dynamics are not a contraction); the bound is the FP64 pipe.
+// One thread owns one environment: its 14 state components are loaded from the component-major (SoA) state array
+// with fully coalesced accesses (a warp reads 256 contiguous bytes per float64 component), stay in registers
+// through the whole adaptive RK45 step, and are written back the same way.  The dynamics are not a contraction:
+// their bound is the FP64 pipe, and no tensor core touches them.  Kernels:
+//   integrate_kernel | post_kernel   r6_step as a pair: the divergent integrator (one-warp CTAs, stage storage in
+//                                    shared memory) and the uniform reward / flags / reset / observation kernel
+//   step_kernel                      the same step fused (small batches, zero-copy host path)
+//   rollout_kernel, rollout_tc_kernel  k steps per launch with the state in registers (Philox / buffer / policy)
+//   policy_kernel, policy_tc5_kernel   the policy MLP alone: float32 FMAs, mma.sync 3xTF32 tiles, or
+//                                    tcgen05.mma + TMEM (r6_mlp_tc.cuh, r6_mlp_tcgen05.cuh)
+//   reset_kernel, sim_raw_kernel, tgo_kernel, gae_kernel, peak_fma_kernel
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
 #include <cuda_runtime.h>

@@ -95,7 +95,7 @@ __device__ __forceinline__ float tanh_f32(float x)
 }
 
 // Warp-collective.  x[13]: this lane's observation (anything if the lane has no live env).  `scratch` is this
-// warp's staging area in shared memory: float [16][33] (the dead Runge–Kutta stage storage is reused).
+// warp's own staging tile in shared memory: float [16][33] (padded rows: conflict-free transposes).
 // Returns this lane's clipped action.
 __device__ __forceinline__ void mlp_policy_tc(const float *__restrict__ W, float *scratch, const float (&x)[kMlpIn],
                                               float &act0, float &act1, float &act2)

@@ -5,7 +5,7 @@ and the `make_env()` wrapper parameters (/root/reference/main_6DOF.py:29-53).  T
 computed with NumPy expressions of the same operand types as the reference's, because the values
 depend on NumPy's promotion rules (`t_free_fall`, `v_max`, `omega_max` carry
 float32 rounding under NumPy >= 2); the kernel only ever sees the resulting numbers.
-`tests/test_params.py` pins them to `tests/golden/constants.npz` (dumped from the reference).
+`tests/test_abi.py::test_params_match_reference_constants` pins them to `tests/golden/constants.npz` (dumped from the reference).
 """
 from __future__ import annotations
 
