@@ -400,3 +400,41 @@ def test_full_size_invariants_1m_envs():
     assert float(env.reward.max()) <= 100 and float(env.reward.min()) >= -1
     assert np.array_equal(env.obs.cpu().numpy(),
                           (env.state.cpu().numpy() / ep.state_normalizer[:, None]).astype(np.float32))
+
+
+def test_episode_statistics_match_reference_population():
+    """Distributional check that does not inject the reference's initial conditions: the in-kernel Philox reset
+    sampler + uniform random actions on the GPU against the 576 first episodes the unmodified reference ran for
+    config2 (same IC box, same action law, different random streams) — fraction ended within 200 steps, mean and
+    spread of the episode length, share of out-of-bounds endings, all within 3 sigma of the 576-episode sample."""
+    import torch
+    g = golden("config2")
+    done = np.concatenate([g["full_done"], g["summ_done"]], 1)
+    oob = np.concatenate([g["full_oob"], g["summ_oob"]], 1)
+    T, n_ref = done.shape
+    first = np.array([np.argmax(done[:, i]) + 1 if done[:, i].any() else 0 for i in range(n_ref)])
+    ended = first > 0
+    ref_len = first[ended]
+    ref_oob = np.array([oob[first[i] - 1, i] for i in range(n_ref) if ended[i]])
+    n = 32768
+    env = make_batch(n, env_params(), seed=2718, debug_buffers=False)
+    env.reset()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(99)
+    length = torch.zeros(n, dtype=torch.int32, device="cuda")
+    was_oob = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for k in range(T):
+        env.step(torch.rand(n, 3, device="cuda", generator=gen) * 2 - 1)
+        fin = ((env.flags & 3) != 0) & (length == 0)
+        length[fin] = k + 1
+        was_oob |= fin & ((env.flags & 2) != 0)
+    torch.cuda.synchronize()
+    L = length.cpu().numpy()
+    e = L > 0
+    ne = int(ended.sum())
+    print(f"reference: ended {ended.mean():.3f}, length {ref_len.mean():.1f} +- {ref_len.std():.1f}, oob {ref_oob.mean():.3f} | "
+          f"gpu: ended {e.mean():.3f}, length {L[e].mean():.1f} +- {L[e].std():.1f}, oob {was_oob.cpu().numpy()[e].mean():.3f}")
+    assert abs(e.mean() - ended.mean()) <= 3 * np.sqrt(ended.mean() * (1 - ended.mean()) / n_ref) + 0.005
+    assert abs(L[e].mean() - ref_len.mean()) <= 3 * ref_len.std() / np.sqrt(ne) + 0.5
+    assert abs(L[e].std() - ref_len.std()) <= 0.15 * ref_len.std()
+    p = ref_oob.mean()
+    assert abs(was_oob.cpu().numpy()[e].mean() - p) <= 3 * np.sqrt(p * (1 - p) / ne) + 0.005
