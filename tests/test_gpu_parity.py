@@ -438,3 +438,34 @@ def test_episode_statistics_match_reference_population():
     assert abs(L[e].std() - ref_len.std()) <= 0.15 * ref_len.std()
     p = ref_oob.mean()
     assert abs(was_oob.cpu().numpy()[e].mean() - p) <= 3 * np.sqrt(p * (1 - p) / ne) + 0.005
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("over", [dict(timestep=0.5), dict(timestep=0.05, reward_shaping_type="velocity")])
+def test_other_timesteps_and_shaping_vs_oracle(split, over):
+    """Non-default configurations through both step paths (fused kernel / kernel pair) against the C oracle:
+    dt = 0.5 s takes the exact-density kernels (the per-step series is only guaranteed up to 0.25 s), dt = 0.05 s
+    with velocity shaping takes the series kernels and the alternative reward."""
+    import torch
+    from oracle import c_oracle as co
+    ep = env_params(**over)
+    n, K = 1024, 40
+    env = make_batch(n, ep, split_step=split, seed=5)
+    env.reset()
+    torch.cuda.synchronize()
+    ic = env.state.t().cpu().numpy()
+    ob = co.OracleBatch(ep, n)
+    ob.set_state(ic, ic[:, 13].astype(np.float32), 0, v0=env.v0.cpu().numpy())
+    rng = np.random.default_rng(8)
+    alive = np.ones(n, bool)
+    for k in range(K):
+        a = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        env.step(torch.from_numpy(a).cuda())
+        o = fetch(env)
+        r = ob.step(a)
+        assert np.array_equal(o["nfev"][alive], r["nfev"][alive]), k
+        assert np.array_equal(o["done"][alive], r["done"][alive].astype(bool)), k
+        assert state_err(o["state"][alive], r["state"][alive], ep.state_normalizer).max() <= RTOL_STATE, k
+        assert reward_err_traj(o["reward"][alive], r["reward"][alive]).max() <= RTOL_REWARD_TRAJ, k
+        alive &= ~o["done"]
+    assert alive.sum() > 0
