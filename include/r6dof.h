@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 11
+#define R6_ABI_VERSION 12
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -151,7 +151,9 @@ typedef struct R6Buffers {
 typedef struct R6Mlp {
     const float *w0, *b0;   /* [128][13], [128] */
     const float *w1, *b1;   /* [64][128], [64]  */
-    const float *w2, *b2;   /* [3][64],  [3]    */
+    const float *w2, *b2;   /* [3][64],  [3]    action_net */
+    const float *wv, *bv;   /* [64], [1] nullable: value_net on the same latent (the critic of the shared-trunk policy) */
+    const float *log_std;   /* [3] nullable: state-independent log standard deviation of the Gaussian policy */
 } R6Mlp;
 
 int r6_abi_version(void);
@@ -228,6 +230,18 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
  * (fast mode, |d action| ~1e-3 vs mode 0).
  */
 int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream);
+
+/*
+ * The full forward pass PPO.collect_rollouts needs (SB3 ActorCriticPolicy.forward): Gaussian mean from action_net,
+ * value from value_net on the same latent, and — when stochastic != 0 — an action sampled as
+ * mean + exp(log_std) * eps with eps ~ N(0, 1) from Philox (seed, global env id, step_index) and its log-probability
+ * (sum over the 3 action dimensions, evaluated on the UNclipped sample like SB3's DiagGaussianDistribution).
+ * actions [n][3]: what the env is stepped with (clipped to [-1, 1]); actions_raw [n][3], values [n], log_prob [n]
+ * are nullable.  stochastic == 0: the deterministic mean (r6_policy) with the value, log_prob of the mean.
+ */
+int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, int32_t stochastic, uint64_t seed,
+                 int64_t env_offset, int64_t step_index, float *actions, float *actions_raw, float *values,
+                 float *log_prob, void *stream);
 
 /*
  * Generalised advantage estimation over a recorded rollout, on the device, so that the PPO update of

@@ -14,7 +14,7 @@ starts = set(int(s) for s in g["ic_step"])
 idx = np.array([k for k in range(1, len(g["action"])) if k not in starts])[:n]
 env.obs[:, :len(idx)] = torch.from_numpy(np.ascontiguousarray(g["obs"][idx - 1].T)).cuda()
 L = _lib.load()
-m = R6Mlp(*[wd[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
+m = _lib.make_mlp(wd)
 out = {}
 for mode in (0, 2):
     a = torch.zeros(n, 3, device="cuda")

@@ -178,7 +178,7 @@ class Rocket6DOFBatch:
         if mode in (ACT_MLP, ACT_MLP_TC):
             if mlp is None:
                 raise ValueError("ACT_MLP needs the policy weights")
-            m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
+            m = _lib.make_mlp(mlp)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.r6_rollout(C.byref(self._p), C.byref(self._b), n, self.env_offset, int(k), int(mode),
                                            C.byref(m) if m is not None else None, ab, self.seed_value,
@@ -206,11 +206,55 @@ class Rocket6DOFBatch:
         2 = tcgen05 + TMEM single-pass TF32 (fast mode, ~1e-3)."""
         if out is None:
             out = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
-        m = R6Mlp(*[mlp[x].data_ptr() for x in ("w0", "b0", "w1", "b1", "w2", "b2")])
+        m = _lib.make_mlp(mlp)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.r6_policy(C.byref(m), self.obs.data_ptr(), self.num_envs, int(tensor_cores),
                                           out.data_ptr(), self._stream()), self.lib)
         return out
+
+    def policy_forward(self, mlp: dict, *, stochastic: bool = False, tensor_cores=False, step_index: Optional[int] = None):
+        """SB3 `ActorCriticPolicy.forward` for the current observations in one launch (`r6_policy_ex`): returns
+        (env_actions [N,3] clipped, raw_actions [N,3], values [N], log_prob [N]).  `mlp` may carry the critic head
+        ("wv", "bv") and the Gaussian "log_std"; stochastic=True samples mean + exp(log_std) eps with Philox noise
+        keyed by (seed, global env id, step_index) — reproducible and independent of the shard count."""
+        n, dev = self.num_envs, self.device
+        act = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        raw = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        val = torch.empty(n, dtype=torch.float32, device=dev)
+        logp = torch.empty(n, dtype=torch.float32, device=dev)
+        m = _lib.make_mlp(mlp)
+        step = self.steps_done if step_index is None else int(step_index)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.r6_policy_ex(C.byref(m), self.obs.data_ptr(), n, int(tensor_cores), int(bool(stochastic)),
+                                             self.seed_value, self.env_offset, step, act.data_ptr(), raw.data_ptr(),
+                                             val.data_ptr(), logp.data_ptr(), self._stream()), self.lib)
+        return act, raw, val, logp
+
+    def collect_rollout(self, k: int, mlp: dict, *, gamma: float = 0.99, gae_lambda: float = 0.95,
+                        stochastic: bool = True, tensor_cores=False) -> dict:
+        """What SB3's `PPO.collect_rollouts` + `RolloutBuffer.compute_returns_and_advantage` produce for k steps of
+        this VecEnv, entirely on the device: per step one policy launch (action, value, log-prob), one env step; then
+        the GAE scan.  Returns tensors shaped [k, N, ...]: obs (13), actions (raw Gaussian samples), values, log_probs,
+        rewards, dones, advantages, returns.  (Bootstrapping time-limit truncations with the critic is left to the
+        caller, as in `gae.compute_gae`.)"""
+        from .gae import compute_gae
+        n, dev = self.num_envs, self.device
+        obs = torch.empty(k, n, 13, dtype=torch.float32, device=dev)
+        acts = torch.empty(k, n, 3, dtype=torch.float32, device=dev)
+        vals = torch.empty(k, n, dtype=torch.float32, device=dev)
+        logp = torch.empty(k, n, dtype=torch.float32, device=dev)
+        rews = torch.empty(k, n, dtype=torch.float32, device=dev)
+        dones = torch.empty(k, n, dtype=torch.uint8, device=dev)
+        for j in range(int(k)):
+            obs[j] = self.obs[:13].t()
+            a_env, a_raw, v, lp = self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores)
+            acts[j], vals[j], logp[j] = a_raw, v, lp
+            self.step(a_env)
+            rews[j], dones[j] = self.reward_f32, self.done
+        _, _, last_v, _ = self.policy_forward(mlp, stochastic=False, tensor_cores=tensor_cores)
+        adv, ret = compute_gae(rews, vals, dones, last_v, gamma, gae_lambda)
+        return dict(obs=obs, actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones, advantages=adv,
+                    returns=ret, last_values=last_v)
 
     def step_policy(self, k: int, mlp: dict, *, tensor_cores=False):
         """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes

@@ -1230,13 +1230,14 @@ R6_HD void philox_action(uint64_t seed, uint64_t genv, uint64_t step, float &a0,
 // (or by the host build in plain memory):
 //     [0, 2048)        W0 rows padded to 16: row j = (w0[j][0..12], b0[j], 0, 0)
 //     [2048, 10240)    W1 transposed: [in j][out k]  (64 contiguous floats per hidden-0 unit)
-//     [10240, 10304)   b1      [10304, 10496)  W2 [3][64]      [10496, 10500)  b2 (+ pad)
+//     [10240, 10304)   b1      [10304, 10560)  W2 [4][64] (row 3 = value head)      [10560, 10564)  b2, bv
 // One thread evaluates the whole network for its environment: hidden-0 units are produced one at a
 // time and immediately scattered into the 64 hidden-1 accumulators, so nothing but those 64 floats
 // is live; every weight read is a warp-uniform (broadcast) 16-byte load.
 constexpr int kMlpIn = 13, kMlpH0 = 128, kMlpH1 = 64, kMlpOut = 3;
 constexpr int kMlpOffW1 = kMlpH0 * 16, kMlpOffB1 = kMlpOffW1 + kMlpH0 * kMlpH1, kMlpOffW2 = kMlpOffB1 + kMlpH1;
-constexpr int kMlpOffB2 = kMlpOffW2 + kMlpOut * kMlpH1, kMlpFloats = kMlpOffB2 + 4;
+constexpr int kMlpRows = 4;       // output rows of the last layer: 3 action means + the value head (0 when absent)
+constexpr int kMlpOffB2 = kMlpOffW2 + kMlpRows * kMlpH1, kMlpFloats = kMlpOffB2 + 4;
 
 struct F4 { float x, y, z, w; };
 R6_HD F4 ld4(const float *p)
@@ -1247,6 +1248,18 @@ R6_HD F4 ld4(const float *p)
 #else
     return F4{p[0], p[1], p[2], p[3]};
 #endif
+}
+
+// last layer as 4 rows: action_net rows 0..2, value_net as row 3 (zeros when the caller gave no critic)
+R6_HD float mlp_w2_row(const R6Mlp &m, int row, int k)
+{
+    if (row < kMlpOut) return m.w2[row * kMlpH1 + k];
+    return (row == kMlpOut && m.wv != nullptr) ? m.wv[k] : 0.0f;
+}
+R6_HD float mlp_b2_row(const R6Mlp &m, int row)
+{
+    if (row < kMlpOut) return m.b2[row];
+    return (row == kMlpOut && m.bv != nullptr) ? m.bv[0] : 0.0f;
 }
 
 // element `idx` of the packed block from the SB3-layout tensors ([out][in] row-major)
@@ -1261,11 +1274,12 @@ R6_HD float mlp_pack_element(const R6Mlp &m, int idx)
         return m.w1[k * kMlpH0 + j];
     }
     if (idx < kMlpOffW2) return m.b1[idx - kMlpOffB1];
-    if (idx < kMlpOffB2) return m.w2[idx - kMlpOffW2];
-    return idx - kMlpOffB2 < kMlpOut ? m.b2[idx - kMlpOffB2] : 0.0f;
+    if (idx < kMlpOffB2) return mlp_w2_row(m, (idx - kMlpOffW2) / kMlpH1, (idx - kMlpOffW2) % kMlpH1);
+    return mlp_b2_row(m, idx - kMlpOffB2);
 }
 
-R6_HD void mlp_policy(const float *W, const float *x, float &a0, float &a1, float &a2)
+// raw outputs: out[0..2] = Gaussian mean (unclipped), out[3] = value
+R6_HD void mlp_forward(const float *W, const float *x, float (&out)[4])
 {
     float acc[kMlpH1];
 #pragma unroll
@@ -1287,18 +1301,58 @@ R6_HD void mlp_policy(const float *W, const float *x, float &a0, float &a1, floa
             acc[k + 2] = f32_fma(w.z, h, acc[k + 2]); acc[k + 3] = f32_fma(w.w, h, acc[k + 3]);
         }
     }
-    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMlpH1; k++) {
         const float h = tanhf(acc[k] + W[kMlpOffB1 + k]);
         o0 = f32_fma(W[kMlpOffW2 + k], h, o0);
         o1 = f32_fma(W[kMlpOffW2 + kMlpH1 + k], h, o1);
         o2 = f32_fma(W[kMlpOffW2 + 2 * kMlpH1 + k], h, o2);
+        o3 = f32_fma(W[kMlpOffW2 + 3 * kMlpH1 + k], h, o3);
     }
-    a0 = fminf(fmaxf(o0 + W[kMlpOffB2], -1.0f), 1.0f);
-    a1 = fminf(fmaxf(o1 + W[kMlpOffB2 + 1], -1.0f), 1.0f);
-    a2 = fminf(fmaxf(o2 + W[kMlpOffB2 + 2], -1.0f), 1.0f);
+    out[0] = o0 + W[kMlpOffB2];
+    out[1] = o1 + W[kMlpOffB2 + 1];
+    out[2] = o2 + W[kMlpOffB2 + 2];
+    out[3] = o3 + W[kMlpOffB2 + 3];
 }
+// deterministic action of evaluate_policy / predict: the mean clipped to the action space
+R6_HD void mlp_policy(const float *W, const float *x, float &a0, float &a1, float &a2)
+{
+    float out[4];
+    mlp_forward(W, x, out);
+    a0 = fminf(fmaxf(out[0], -1.0f), 1.0f);
+    a1 = fminf(fmaxf(out[1], -1.0f), 1.0f);
+    a2 = fminf(fmaxf(out[2], -1.0f), 1.0f);
+}
+
+// Gaussian policy head (SB3 DiagGaussianDistribution with a state-independent log_std): sample and log-probability.
+// eps from one Philox block keyed (seed, global env, step) through Box-Muller.
+constexpr uint32_t kStreamPolicy = 0x50414354u;   // 'PACT'
+R6_HD void gaussian_head(const float (&mean)[4], const float *log_std, bool stochastic, uint64_t seed, uint64_t genv,
+                         uint64_t step, float (&raw)[3], float &logp)
+{
+    float z[3] = {0.0f, 0.0f, 0.0f};
+    if (stochastic) {
+        U4 ctr = {(uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)step, kStreamPolicy ^ (uint32_t)(step >> 32)};
+        const U4 r = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float s = 1.0f / 4294967296.0f;
+        const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)r.y * s;
+        const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = (float)r.w * s;
+        const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+        z[0] = ra * cosf(6.283185307179586f * u2);
+        z[1] = ra * sinf(6.283185307179586f * u2);
+        z[2] = rb * cosf(6.283185307179586f * u4);
+    }
+    logp = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float ls = log_std != nullptr ? log_std[i] : 0.0f;
+        raw[i] = mean[i] + expf(ls) * z[i];
+        logp += -0.5f * z[i] * z[i] - ls - 0.9189385332046727f;      // 0.5 log(2 pi)
+    }
+}
+
+
 
 // ------------------------------------------------------------------------------------------------
 // Registers carried by the thread that owns an environment, and the glue of one env step

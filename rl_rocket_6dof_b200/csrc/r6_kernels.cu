@@ -468,12 +468,32 @@ tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int6
     if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i]);
 }
 
-// The policy as its own kernel (r6_policy): uniform work, no integrator state => small code, high occupancy.
-// Persistent: the grid is one wave of CTAs, each packs the weights into shared memory ONCE (the gather with its
-// index arithmetic costs as much as one network evaluation) and then walks over its tiles of 128 envs.
+// What a policy launch writes besides the env actions, and how the action is chosen (r6_policy_ex)
+struct PolicyOut {
+    float *actions, *raw, *values, *logp;     // [n][3] clipped, [n][3] nullable, [n] nullable, [n] nullable
+    int stochastic;
+    uint64_t seed;
+    int64_t env_offset, step;
+};
+__device__ __forceinline__ void policy_epilogue(const PolicyOut &po, const float *log_std, int64_t i, const float (&out)[4])
+{
+    float raw[3], logp;
+    gaussian_head(out, log_std, po.stochastic != 0, po.seed, (uint64_t)(po.env_offset + i), (uint64_t)po.step, raw, logp);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        po.actions[3 * i + c] = fminf(fmaxf(raw[c], -1.0f), 1.0f);
+        if (po.raw) po.raw[3 * i + c] = raw[c];
+    }
+    if (po.values) po.values[i] = out[3];
+    if (po.logp) po.logp[i] = logp;
+}
+
+// The policy as its own kernel (r6_policy / r6_policy_ex): uniform work, no integrator state => small code, high
+// occupancy.  Persistent: the grid is one wave of CTAs, each packs the weights into shared memory ONCE (the gather
+// with its index arithmetic costs as much as one network evaluation) and then walks over its tiles of 128 envs.
 template <bool kTc>
 __global__ void __launch_bounds__(kThreads, kTc ? 3 : 4)
-policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *__restrict__ actions)
+policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
     extern __shared__ double r6_smem[];
     float *Ws = reinterpret_cast<float *>(r6_smem);
@@ -483,12 +503,12 @@ policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *
     const int64_t tiles = (n + kThreads - 1) / kThreads;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t i = tile * kThreads + threadIdx.x;
-        float x[kMlpIn], a0, a1, a2;
+        float x[kMlpIn], out[4];
 #pragma unroll
         for (int c = 0; c < kMlpIn; c++) x[c] = i < n ? obs[(int64_t)c * n + i] : 0.0f;
-        if (kTc) mlp_policy_tc(Ws, Ws + kMlpTcFloats + (threadIdx.x >> 5) * (16 * 33), x, a0, a1, a2);
-        else mlp_policy(Ws, x, a0, a1, a2);
-        if (i < n) { actions[3 * i] = a0; actions[3 * i + 1] = a1; actions[3 * i + 2] = a2; }
+        if (kTc) mlp_forward_tc(Ws, Ws + kMlpTcFloats + (threadIdx.x >> 5) * (16 * 33), x, out);
+        else mlp_forward(Ws, x, out);
+        if (i < n) policy_epilogue(po, mlp.log_std, i, out);
     }
 }
 constexpr int kSmemPolicyTc = (r6::kMlpTcFloats + (kThreads / 32) * 16 * 33) * (int)sizeof(float);
@@ -496,7 +516,7 @@ constexpr int kSmemPolicy = r6::kMlpFloats * (int)sizeof(float);
 
 // The policy on tcgen05 / TMEM (r6_policy tensor_cores = 2, fast single-pass TF32 mode): see r6_mlp_tcgen05.cuh.
 __global__ void __launch_bounds__(tc5::kTile, 2)
-policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, float *__restrict__ actions)
+policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
     using namespace tc5;
     extern __shared__ double r6_smem[];
@@ -513,12 +533,12 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, flo
     }
     for (int idx = tid; idx < 16 * 64; idx += kTile) {
         const int r = idx >> 6, k = idx & 63;
-        *reinterpret_cast<float *>(S + kOffW2 + tile_off(r, k, 64)) = r < kMlpOut ? round_tf32(mlp.w2[r * kMlpH1 + k]) : 0.0f;
+        *reinterpret_cast<float *>(S + kOffW2 + tile_off(r, k, 64)) = r < kMlpRows ? round_tf32(mlp_w2_row(mlp, r, k)) : 0.0f;
     }
     float *bias = reinterpret_cast<float *>(S + kOffBias);
     bias[tid] = mlp.b0[tid];
     if (tid < 64) bias[128 + tid] = mlp.b1[tid];
-    if (tid < 4) bias[192 + tid] = tid < kMlpOut ? mlp.b2[tid] : 0.0f;
+    if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
     const uint32_t bar = smem_u32(S + kOffBar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -572,9 +592,8 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, flo
             float v[32];
             tmem_ld32(tmem_row + kColD2, v);
             if (i < n) {
-                actions[3 * i] = fminf(fmaxf(v[0] + bias[192], -1.0f), 1.0f);
-                actions[3 * i + 1] = fminf(fmaxf(v[1] + bias[193], -1.0f), 1.0f);
-                actions[3 * i + 2] = fminf(fmaxf(v[2] + bias[194], -1.0f), 1.0f);
+                const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
+                policy_epilogue(po, mlp.log_std, i, out);
             }
         }
     }
@@ -826,29 +845,37 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
     return check_launch("r6_tgo");
 }
 
-int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream)
+int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, int32_t stochastic, uint64_t seed,
+                 int64_t env_offset, int64_t step_index, float *actions, float *actions_raw, float *values,
+                 float *log_prob, void *stream)
 {
     if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
         return fail(R6_EINVAL, "policy weights are null%s");
     if (!obs || !actions) return fail(R6_EINVAL, "null pointer%s");
     if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (tensor_cores < 0 || tensor_cores > 2) return fail(R6_EINVAL, "tensor_cores must be 0, 1 or 2%s");
     if (n == 0) return R6_OK;
     int rc = ensure_attributes();
     if (rc) return rc;
-    // one resident wave: SM count x resident CTAs per SM (3 with the tensor-core tiles' registers, 4 otherwise)
+    // one resident wave: SM count x resident CTAs per SM
     static thread_local int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
-    if (tensor_cores < 0 || tensor_cores > 2) return fail(R6_EINVAL, "tensor_cores must be 0, 1 or 2%s");
+    const PolicyOut po = {actions, actions_raw, values, log_prob, stochastic, seed, env_offset, step_index};
     const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
     const unsigned g = (unsigned)(blocks_for(n) < wave ? blocks_for(n) : wave);
-    if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
-    else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
-    else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, actions);
+    if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+    else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+    else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     return check_launch("r6_policy");
+}
+
+int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream)
+{
+    return r6_policy_ex(mlp, obs, n, tensor_cores, 0, 0, 0, 0, actions, nullptr, nullptr, nullptr, stream);
 }
 
 int r6_gae(const float *rew, const float *values, const uint8_t *done, const float *last_values, int32_t T, int64_t n,

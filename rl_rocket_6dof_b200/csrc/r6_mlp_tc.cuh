@@ -53,9 +53,9 @@ __device__ __forceinline__ float mlp_tc_pack_element(const R6Mlp &m, int idx)
     if (idx < kTcOffB2) {
         const int r = idx - kTcOffW2, e = r & 1, lane = (r >> 1) & 31, j = r >> 6;
         const int g = lane >> 2, t = lane & 3;
-        return g < kMlpOut ? m.w2[g * kMlpH1 + 8 * j + 2 * t + e] : 0.0f;
+        return g < kMlpRows ? mlp_w2_row(m, g, 8 * j + 2 * t + e) : 0.0f;
     }
-    return idx - kTcOffB2 < kMlpOut ? m.b2[idx - kTcOffB2] : 0.0f;
+    return mlp_b2_row(m, idx - kTcOffB2);
 }
 
 struct Split { uint32_t hi, lo; };
@@ -96,9 +96,9 @@ __device__ __forceinline__ float tanh_f32(float x)
 
 // Warp-collective.  x[13]: this lane's observation (anything if the lane has no live env).  `scratch` is this
 // warp's own staging tile in shared memory: float [16][33] (padded rows: conflict-free transposes).
-// Returns this lane's clipped action.
-__device__ __forceinline__ void mlp_policy_tc(const float *__restrict__ W, float *scratch, const float (&x)[kMlpIn],
-                                              float &act0, float &act1, float &act2)
+// Returns this lane's raw outputs: out[0..2] = Gaussian mean (unclipped), out[3] = value.
+__device__ __forceinline__ void mlp_forward_tc(const float *__restrict__ W, float *scratch, const float (&x)[kMlpIn],
+                                               float (&out)[4])
 {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     // ---- transpose the observations into A fragments through shared memory: scratch[c][env] ----
@@ -159,8 +159,8 @@ __device__ __forceinline__ void mlp_policy_tc(const float *__restrict__ W, float
     // ---- layer 2: 64 -> 3 (n-tile padded to 8) ----
     float o[2][4];
     {
-        const float bx = (2 * t < kMlpOut) ? W[kTcOffB2 + 2 * t] : 0.0f;
-        const float by = (2 * t + 1 < kMlpOut) ? W[kTcOffB2 + 2 * t + 1] : 0.0f;
+        const float bx = (2 * t < kMlpRows) ? W[kTcOffB2 + 2 * t] : 0.0f;
+        const float by = (2 * t + 1 < kMlpRows) ? W[kTcOffB2 + 2 * t + 1] : 0.0f;
 #pragma unroll
         for (int m = 0; m < 2; m++) { o[m][0] = bx; o[m][1] = by; o[m][2] = bx; o[m][3] = by; }
     }
@@ -190,10 +190,21 @@ __device__ __forceinline__ void mlp_policy_tc(const float *__restrict__ W, float
         }
     }
     __syncwarp();
-    act0 = fminf(fmaxf(scratch[0 * 33 + lane], -1.0f), 1.0f);
-    act1 = fminf(fmaxf(scratch[1 * 33 + lane], -1.0f), 1.0f);
-    act2 = fminf(fmaxf(scratch[2 * 33 + lane], -1.0f), 1.0f);
+    out[0] = scratch[0 * 33 + lane];
+    out[1] = scratch[1 * 33 + lane];
+    out[2] = scratch[2 * 33 + lane];
+    out[3] = scratch[3 * 33 + lane];
     __syncwarp();
+}
+// deterministic action (clipped mean)
+__device__ __forceinline__ void mlp_policy_tc(const float *__restrict__ W, float *scratch, const float (&x)[kMlpIn],
+                                              float &act0, float &act1, float &act2)
+{
+    float out[4];
+    mlp_forward_tc(W, scratch, x, out);
+    act0 = fminf(fmaxf(out[0], -1.0f), 1.0f);
+    act1 = fminf(fmaxf(out[1], -1.0f), 1.0f);
+    act2 = fminf(fmaxf(out[2], -1.0f), 1.0f);
 }
 
 }  // namespace r6

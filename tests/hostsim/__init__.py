@@ -81,7 +81,8 @@ def mlp_actions(weights, obs13):
     from rl_rocket_6dof_b200._lib import R6Mlp
     L = lib()
     w = {k: np.ascontiguousarray(v, np.float32) for k, v in weights.items()}
-    m = R6Mlp(*[w[k].ctypes.data for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+    from rl_rocket_6dof_b200._lib import make_mlp
+    m = make_mlp(w)
     W = np.zeros(L.hs_mlp_floats(), np.float32)
     L.hs_mlp_pack(C.byref(m), W.ctypes.data)
     x = np.ascontiguousarray(obs13, np.float32).reshape(-1, 13)

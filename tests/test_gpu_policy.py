@@ -234,3 +234,73 @@ def test_one_episode_rollout_freezes_finished_envs():
     env.rollout(4, ACT_PHILOX)
     torch.cuda.synchronize()
     assert int(env.step_count.min()) == 4 and not bool(env.done.any())
+
+
+def _actor_critic_weights():
+    from rl_rocket_6dof_b200 import policy
+    w = policy.load_npz(GOLD)
+    rng = np.random.default_rng(5)
+    w["wv"] = (rng.standard_normal(64) * 0.3).astype(np.float32)       # the fixture holds the actor only
+    w["bv"] = np.array([0.7], np.float32)
+    w["log_std"] = np.array([-0.5, -1.0, 0.2], np.float32)
+    return w
+
+
+@pytest.mark.parametrize("tensor_cores,tol", [(0, 3e-6), (1, 5e-6), (2, 1e-2)])
+def test_actor_critic_forward_value_and_gaussian_sampling(tensor_cores, tol):
+    """r6_policy_ex: value head on the shared latent, Gaussian sampling with Philox noise, SB3's log-probability."""
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    g = np.load(GOLD)
+    w = _actor_critic_weights()
+    n = 8739
+    env = Rocket6DOFBatch(n, params=env_params(), device="cuda:0", seed=31)
+    wd = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    x = g["obs"][:n, :13]
+    env.obs[:13].copy_(torch.from_numpy(np.ascontiguousarray(x.T)))
+    mean_ref, val_ref = policy.forward_full_numpy(w, x)
+    # deterministic: action = clipped mean, log-prob of the mean, value
+    a, raw, v, lp = (t.cpu().numpy() for t in env.policy_forward(wd, stochastic=False, tensor_cores=tensor_cores))
+    assert np.abs(raw - mean_ref).max() <= tol and np.abs(v - val_ref).max() <= 4 * tol
+    assert np.array_equal(a, np.clip(raw, -1, 1))
+    assert np.allclose(lp, -(w["log_std"].sum() + 3 * 0.9189385332046727), atol=1e-5)
+    # stochastic: eps = (raw - mean) / std is standard normal, log-prob is SB3's formula, streams are reproducible
+    a, raw, v, lp = (t.cpu().numpy() for t in env.policy_forward(wd, stochastic=True, tensor_cores=tensor_cores, step_index=7))
+    std = np.exp(w["log_std"])
+    eps = (raw - mean_ref) / std
+    if tensor_cores != 2:
+        ref_lp = (-0.5 * eps.astype(np.float64) ** 2 - w["log_std"] - 0.9189385332046727).sum(1)
+        assert np.abs(lp - ref_lp).max() <= 2e-3
+    assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1) < 0.02
+    assert abs(np.corrcoef(eps[:, 0], eps[:, 1])[0, 1]) < 0.04 and abs(np.corrcoef(eps[:-1, 2], eps[1:, 2])[0, 1]) < 0.04
+    assert (np.abs(eps) > 3).mean() < 0.006
+    a2, raw2, _, _ = (t.cpu().numpy() for t in env.policy_forward(wd, stochastic=True, tensor_cores=tensor_cores, step_index=7))
+    assert np.array_equal(raw, raw2)
+    _, raw3, _, _ = (t.cpu().numpy() for t in env.policy_forward(wd, stochastic=True, tensor_cores=tensor_cores, step_index=8))
+    assert not np.array_equal(raw, raw3)
+
+
+def test_collect_rollout_on_device():
+    """collect_rollout = policy_forward + step per env-step, then the GAE scan; checked against the pieces."""
+    import torch
+    from oracle import gae_oracle
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    w = _actor_critic_weights()
+    wd = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    n, k = 2048, 48
+    env = Rocket6DOFBatch(n, params=env_params(), device="cuda:0", seed=3)
+    env.reset()
+    ro = env.collect_rollout(k, wd, gamma=0.99, gae_lambda=0.95, stochastic=True)
+    torch.cuda.synchronize()
+    assert ro["obs"].shape == (k, n, 13) and ro["actions"].shape == (k, n, 3) and ro["advantages"].shape == (k, n)
+    mean, val = policy.forward_full_numpy(w, ro["obs"].cpu().numpy().reshape(-1, 13))
+    assert np.abs(val.reshape(k, n) - ro["values"].cpu().numpy()).max() <= 2e-5
+    eps = (ro["actions"].cpu().numpy().reshape(-1, 3) - mean) / np.exp(w["log_std"])
+    assert abs(eps.mean()) < 0.01 and abs(eps.std() - 1) < 0.01
+    adv, ret = gae_oracle.compute_returns_and_advantage(ro["rewards"].cpu().numpy(), ro["values"].cpu().numpy(),
+                                                        ro["dones"].cpu().numpy() != 0, ro["last_values"].cpu().numpy(),
+                                                        0.99, 0.95)
+    assert np.array_equal(adv, ro["advantages"].cpu().numpy()) and np.array_equal(ret, ro["returns"].cpu().numpy())
+    assert float(env.stats[7]) == n * k
