@@ -212,16 +212,20 @@ class Rocket6DOFBatch:
                                           out.data_ptr(), self._stream()), self.lib)
         return out
 
-    def policy_forward(self, mlp: dict, *, stochastic: bool = False, tensor_cores=False, step_index: Optional[int] = None):
+    def policy_forward(self, mlp: dict, *, stochastic: bool = False, tensor_cores=False, step_index: Optional[int] = None,
+                       out: Optional[tuple] = None):
         """SB3 `ActorCriticPolicy.forward` for the current observations in one launch (`r6_policy_ex`): returns
         (env_actions [N,3] clipped, raw_actions [N,3], values [N], log_prob [N]).  `mlp` may carry the critic head
         ("wv", "bv") and the Gaussian "log_std"; stochastic=True samples mean + exp(log_std) eps with Philox noise
         keyed by (seed, global env id, step_index) — reproducible and independent of the shard count."""
         n, dev = self.num_envs, self.device
-        act = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        raw = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        val = torch.empty(n, dtype=torch.float32, device=dev)
-        logp = torch.empty(n, dtype=torch.float32, device=dev)
+        if out is not None:                      # (act, raw, val, logp) contiguous float32 CUDA tensors to write into
+            act, raw, val, logp = out
+        else:
+            act = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            raw = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            val = torch.empty(n, dtype=torch.float32, device=dev)
+            logp = torch.empty(n, dtype=torch.float32, device=dev)
         m = _lib.make_mlp(mlp)
         step = self.steps_done if step_index is None else int(step_index)
         with torch.cuda.device(dev):
@@ -245,10 +249,10 @@ class Rocket6DOFBatch:
         logp = torch.empty(k, n, dtype=torch.float32, device=dev)
         rews = torch.empty(k, n, dtype=torch.float32, device=dev)
         dones = torch.empty(k, n, dtype=torch.uint8, device=dev)
+        a_env = torch.empty(n, 3, dtype=torch.float32, device=dev)
         for j in range(int(k)):
             obs[j] = self.obs[:13].t()
-            a_env, a_raw, v, lp = self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores)
-            acts[j], vals[j], logp[j] = a_raw, v, lp
+            self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores, out=(a_env, acts[j], vals[j], logp[j]))
             self.step(a_env)
             rews[j], dones[j] = self.reward_f32, self.done
         _, _, last_v, _ = self.policy_forward(mlp, stochastic=False, tensor_cores=tensor_cores)

@@ -1338,10 +1338,20 @@ R6_HD void gaussian_head(const float (&mean)[4], const float *log_std, bool stoc
         const float s = 1.0f / 4294967296.0f;
         const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)r.y * s;
         const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = (float)r.w * s;
+#if defined(__CUDA_ARCH__)
+        // MUFU log / sin / cos: the arguments are in [0, 2 pi) and (0, 1], where the fast units are good to ~1e-6
+        const float ra = sqrtf(-2.0f * __logf(u1)), rb = sqrtf(-2.0f * __logf(u3));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        z[0] = ra * cs;
+        z[1] = ra * sn;
+        z[2] = rb * __cosf(6.283185307179586f * u4);
+#else
         const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
         z[0] = ra * cosf(6.283185307179586f * u2);
         z[1] = ra * sinf(6.283185307179586f * u2);
         z[2] = rb * cosf(6.283185307179586f * u4);
+#endif
     }
     logp = 0.0f;
 #pragma unroll
