@@ -336,6 +336,24 @@ def run_b200(args):
         ms_two[tc] = max_over_ranks(e0.elapsed_time(e1))
         barrier()
 
+    # PPO rollout collection on the device: stochastic Gaussian policy (tcgen05 mode) + value head + env step per
+    # step, then the GAE scan — what SB3's collect_rollouts / compute_returns_and_advantage do on the host
+    wac = dict(wts)
+    if "wv" not in wac:
+        g1 = np.random.default_rng(1)
+        wac.update(wv=(g1.standard_normal(64) * 0.3).astype(np.float32), bv=np.zeros(1, np.float32),
+                   log_std=np.array([-1.44, -2.07, -2.01], np.float32))
+    wacd = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in wac.items()}
+    KC = max(min(K, 32), 1)
+    env.collect_rollout(KC, wacd, tensor_cores=2)          # also warms the allocator for the [KC, N, ...] buffers
+    barrier()
+    e0.record(stream)
+    env.collect_rollout(KC, wacd, tensor_cores=2)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_collect = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+
     # ---- end to end through the VecEnv fast path (host actions in, host obs/reward/done out) --
     for w in range(W):
         vec.step_host(acts_h[w % R])
@@ -427,6 +445,9 @@ def run_b200(args):
                                             "ms_per_step": ms_two[2] / K, "launches_per_step": 2,
                                             "actions": "r6_policy (tcgen05.mma kind::tf32, TMEM accumulators, single-pass TF32: "
                                                        "|d action| ~1e-3) then r6_step"},
+        "ppo_collect_rollout": {"value": world * n * KC / (ms_collect * 1e-3), "unit": UNIT, "ms_per_step": ms_collect / KC,
+                                "steps": KC, "what": "stochastic Gaussian policy + value head (r6_policy_ex, tcgen05 mode), r6_step, "
+                                                     "[T,N] buffers written on the device, then the GAE scan (r6_gae)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},
