@@ -142,3 +142,29 @@ def test_step_random_equals_fused_rollout():
     assert float(((a.state - b.state).abs() / norm).max()) <= 1e-11       # different kernels: FMA contraction may differ
     sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
     assert np.array_equal(sa[[0, 2, 3, 4, 5, 6, 7]], sb[[0, 2, 3, 4, 5, 6, 7]]) and a.steps_done == b.steps_done == 90
+
+
+def test_exact_density_variants_of_the_rollout_kernels():
+    """dt = 0.5 s selects the kExact instantiations (true pow density): fused Philox rollout == step-by-step with the
+    same actions, and the tensor-core policy request falls back to the float32 network (no exact tensor-core kernel)."""
+    import torch
+    import philox_ref as pr
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import ACT_MLP, ACT_MLP_TC
+    import os
+    ep = env_params(timestep=0.5)
+    n, K, seed = 700, 25, 99
+    a, b = _mk(n, params=ep, seed=seed), _mk(n, params=ep, seed=seed)
+    a.reset(); b.reset()
+    a.rollout(K, fused=True)
+    for j in range(K):
+        b.step(torch.from_numpy(pr.actions(seed, np.arange(n), j)).cuda())
+    torch.cuda.synchronize()
+    norm = torch.as_tensor(ep.state_normalizer, device="cuda")[:, None]
+    assert torch.equal(a.episode_id, b.episode_id) and float(((a.state - b.state).abs() / norm).max()) <= 1e-11
+    w = policy.to_device(policy.load_npz(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_cl.npz")), "cuda:0")
+    c, d = _mk(n, params=ep, seed=seed), _mk(n, params=ep, seed=seed)
+    c.reset(); d.reset()
+    c.rollout(K, ACT_MLP, mlp=w); d.rollout(K, ACT_MLP_TC, mlp=w)
+    torch.cuda.synchronize()
+    assert torch.equal(c.state, d.state)
