@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 12
+#define R6_ABI_VERSION 13
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -112,7 +112,9 @@ typedef struct R6Params {
     double va_threshold;        /* VerticalAttitudeReward threshold_height (1e-3) */
     double va_weight;           /* VerticalAttitudeReward weight (-0.5) */
     float xi;                   /* RewardAnnealing thrust penalty (reward_coeff["xi"], default 0.01) */
-    int32_t reserved;
+    int32_t obs_row_major;      /* r6_step (fused kernel) only: write obs[] as [n][obs_rows] row-major — the array a VecEnv
+                                   returns — instead of component-major; each warp stages its 32 x obs_rows block through
+                                   shared memory and stores it as one contiguous run (meant for obs[] in mapped host memory) */
 } R6Params;
 
 /* Device pointers. n = number of local envs. Nullable members are marked. */

@@ -172,6 +172,34 @@ reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, i
     if (b.done) b.done[i] = 0;          // un-freezes the env for one-episode (auto_reset = 0) rollouts
 }
 
+// Row-major observation block of one warp: the 32 x rows floats of the warp's envs are contiguous in a [n][rows]
+// array.  Each lane parks its row in the warp's (by now dead) stage-storage columns, then the warp streams the block
+// out with fully coalesced 128-byte stores.  Warp-collective: call with every lane, `valid` = this lane has an env.
+template <class R>
+__device__ __forceinline__ void write_obs_rows(float *obs, int64_t first_env, int rows, bool valid, const float (&ob)[14],
+                                               R *stage_warp /* smem + first thread of the warp */)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned live = __ballot_sync(0xffffffffu, valid);
+    const int n_valid = __popc(live);                       // valid lanes are a prefix (contiguous env indices)
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 14; c++)
+        if (c < rows) *reinterpret_cast<float *>(&stage_warp[c * kThreads + lane]) = ob[c];
+    __syncwarp();
+    float *dst = obs + first_env * rows;
+    const int total = n_valid * rows;
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+        const int el = lane + 32 * k;
+        if (k < rows && el < total) {
+            const int env = el / rows, c = el - env * rows;
+            dst[el] = *reinterpret_cast<const float *>(&stage_warp[c * kThreads + env]);
+        }
+    }
+    __syncwarp();
+}
+
 template <class R, bool kExact>
 __global__ void __launch_bounds__(kThreads, min_blocks<R>())
 step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
@@ -179,6 +207,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     KStore<R> K = make_kstore<R>();
+    float ob[14];
     if (i < n) {
         EnvT<R> e;
         env_load(b, n, i, e);
@@ -205,9 +234,16 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
                 env_reset(p, b, seed, env_offset + i, e);
             }
         }
-        write_obs(b.obs, n, i, p, dv, e.y);
+        if (p.obs_row_major) {
+#pragma unroll
+            for (int c = 0; c < 14; c++) ob[c] = obs_component(p, dv, e.y, c);
+        } else
+            write_obs(b.obs, n, i, p, dv, e.y);
         env_store(b, n, i, e);
     }
+    if (p.obs_row_major)
+        write_obs_rows<R>(b.obs, (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31), p.obs_rows > 0 ? p.obs_rows : 14, i < n, ob,
+                          K.base - (threadIdx.x & 31));
     if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
 }
 

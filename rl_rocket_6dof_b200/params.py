@@ -66,7 +66,7 @@ class R6Params(C.Structure):
         ("va_threshold", C.c_double),
         ("va_weight", C.c_double),
         ("xi", C.c_float),
-        ("reserved", C.c_int32),
+        ("obs_row_major", C.c_int32),
     ]
 
 
@@ -103,7 +103,7 @@ class EnvParams:
 
     def to_struct(self, auto_reset: bool = True, clip_reward: bool | None = None,
                   time_limit: bool = True, obs_rows: int = 0, precision: int = 0, reward_annealing: bool = False,
-                  vertical_attitude_reward=None) -> R6Params:
+                  vertical_attitude_reward=None, obs_row_major: bool = False) -> R6Params:
         """reward_annealing: RewardAnnealing wrapper (xi = reward_coeff.get("xi", 0.01), wrappers.py:42);
         vertical_attitude_reward: None or (threshold_height, weight) of VerticalAttitudeReward (wrappers.py:129)."""
         p = R6Params()
@@ -140,6 +140,7 @@ class EnvParams:
         p.xi = np.float32(rc.get("xi", 0.01))
         th, wt = vertical_attitude_reward if vertical_attitude_reward is not None else (1e-3, -0.5)
         p.va_threshold, p.va_weight = float(th), float(wt)
+        p.obs_row_major = int(bool(obs_row_major))
         return p
 
 

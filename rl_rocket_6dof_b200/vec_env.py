@@ -65,11 +65,13 @@ class Rocket6DOFVecEnv:
             # same device state, but the per-step outputs land in the pinned host buffers (UVA: a pinned
             # torch tensor's data_ptr() is valid on the device) and only `obs_dim` observation rows are written
             b = self.batch
-            self._p_host = b.params.to_struct(**{**b._struct_kw, "obs_rows": self.obs_dim})
+            # the kernel writes the observations row-major [N, obs_dim] — the array the VecEnv protocol returns
+            self._p_host = b.params.to_struct(**{**b._struct_kw, "obs_rows": self.obs_dim, "obs_row_major": True})
+            self._obs_rm = torch.empty(n, self.obs_dim, dtype=torch.float32).pin_memory()
             hb = type(b._b)()
             for name, _ in hb._fields_:
                 setattr(hb, name, getattr(b._b, name))
-            hb.obs, hb.reward, hb.reward_f32 = self._obs_h.data_ptr(), 0, self._rew_h.data_ptr()
+            hb.obs, hb.reward, hb.reward_f32 = self._obs_rm.data_ptr(), 0, self._rew_h.data_ptr()
             hb.done, hb.flags = self._done_h.data_ptr(), self._flags_h.data_ptr()
             # one fused kernel here, not the integrator | post-step pair: its PCIe writes then overlap the
             # integration of other warps (1.27 ms per 2^20-env step vs 1.64 ms with the split, which would also
@@ -102,7 +104,7 @@ class Rocket6DOFVecEnv:
                                          a.data_ptr(), b.seed_value, b._stream()), b.lib)
             b.steps_done += 1
             torch.cuda.current_stream(b.device).synchronize()
-            return self._obs_h.numpy().T, self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
+            return self._obs_rm.numpy(), self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
         if a.is_pinned():                      # caller already staged the actions in pinned memory
             self._act_d.copy_(a, non_blocking=True)
         else:
@@ -127,7 +129,7 @@ class Rocket6DOFVecEnv:
         obs, rews, dones = self.step_host(self._actions)
         # [N, obs_dim] contiguous: torch's blocked transpose-copy of the pinned [obs_dim, N] buffer is several times
         # faster than numpy's strided copy
-        obs = self._obs_h.t().contiguous().numpy()
+        obs = obs.copy() if obs.flags["C_CONTIGUOUS"] else self._obs_h.t().contiguous().numpy()
         # info dicts are only materialised for envs that finished; the others get a per-env empty dict that is
         # created once and handed out again every step (the protocol does not ask for fresh objects)
         infos: List[dict] = list(self._empty_infos)
