@@ -90,9 +90,11 @@ class Rocket6DOFVecEnv:
         return self._obs_h.numpy().T          # [N, obs_dim] view (strided)
 
     def step_host(self, actions) -> tuple:
-        """actions: [N,3] float32 (numpy or CPU tensor).  Host->device copy of the actions, one step
-        kernel, device->host copy of obs / reward / done / flags; returns numpy views of the pinned
-        buffers (valid until the next call): obs [N, obs_dim], rewards [N] f32, dones [N] bool."""
+        """actions: [N,3] float32 (numpy or CPU tensor).  Returns numpy views of the pinned buffers (valid until
+        the next call): obs [N, obs_dim], rewards [N] f32, dones [N] bool.  zero_copy=True: one kernel that reads the
+        (pinned) actions and writes obs / reward / done / flags straight to host memory over PCIe — the device-side
+        `batch.obs` is then NOT refreshed (use `batch.step` / `batch.policy_*` for device-resident loops).
+        zero_copy=False: host->device copy, step kernels, device->host copies."""
         b = self.batch
         a = torch.as_tensor(actions, dtype=torch.float32).reshape(self.num_envs, 3)
         if self.zero_copy:
