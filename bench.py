@@ -199,6 +199,8 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from rl_rocket_6dof_b200 import sharding as _sharding
+    numa_node = _sharding.bind_to_gpu_numa_node(local) if world > 1 else None    # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -451,6 +453,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
                 "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},
+        "numa_node_rank0": numa_node,
         "episode_stats": {k: sd[k] for k in ("episodes", "mean_return", "mean_length", "landing_rate", "steps")},
         "clocks": clocks,
     }
