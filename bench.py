@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preroll", type=int, default=256, help="untimed env-steps to reach the steady-state episode mix")
+    ap.add_argument("--lanes", type=int, default=2, help="CUDA streams each GPU's env range is stepped on (r6_step_range)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=32768)
     ap.add_argument("--cpu-sample-steps", type=int, default=100)
@@ -219,7 +220,7 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     # index-range sharding: rank r owns global envs [r*n, (r+1)*n); no data-path collective
     vec = Rocket6DOFVecEnv(n, device=dev, seed=42, env_offset=rank * n, num_envs_global=world * n,
-                           record_attempts=True)
+                           record_attempts=True, lanes=args.lanes)
     env = vec.batch
     L = env.lib
     env.reset()
@@ -231,8 +232,10 @@ def run_b200(args):
     stream = torch.cuda.current_stream(dev)
 
     # ---- device-resident throughput: one r6_step launch per env-step -------------------------
+    # With stream lanes the K steps run free on the lane streams (each lane forks from `stream` after e0) and are
+    # joined back into `stream` before e1; the second measurement joins every step (outputs consumable per step).
     for w in range(W):
-        env.step(acts[w % R])
+        env.step(acts[w % R], join=False)
     env.reset_stats()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -240,10 +243,18 @@ def run_b200(args):
     att_sum = torch.zeros((), dtype=torch.float64, device=dev)
     e0.record(stream)
     for k in range(K):
-        env.step(acts[k % R])
+        env.step(acts[k % R], join=False)
+    env.join()
     e1.record(stream)
     torch.cuda.synchronize()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    e0.record(stream)
+    for k in range(K):
+        env.step(acts[k % R])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_joined = max_over_ranks(e0.elapsed_time(e1))
     barrier()
     ms_step = ms_total / K
     value = world * n * K / (ms_total * 1e-3)
@@ -280,15 +291,17 @@ def run_b200(args):
     # ---- optional float32 dynamics path (own error bound, tests/test_gpu_fp32.py): same workload ----
     from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
     env32 = Rocket6DOFBatch(n, device=dev, seed=42, env_offset=rank * n, num_envs_global=world * n, precision="fp32",
-                            record_attempts=True)
+                            record_attempts=True, lanes=args.lanes)
     env32.reset()
     env32.rollout(args.preroll)
     for w in range(W):
-        env32.step(acts[w % R])
+        env32.step(acts[w % R], join=False)
+    env32.join()
     barrier()
     e0.record(stream)
     for k in range(K):
-        env32.step(acts[k % R])
+        env32.step(acts[k % R], join=False)
+    env32.join()
     e1.record(stream)
     torch.cuda.synchronize()
     ms_f32 = max_over_ranks(e0.elapsed_time(e1))
@@ -405,16 +418,24 @@ def run_b200(args):
                                f"U[-1,1] f32 resident in HBM, auto-reset on, make_env() wrappers fused",
                    "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"index-range shards x{world}",
                    "l2": "per-step working set 336 B x envs = %.0f MB > 126 MB L2" % (n * 336 / 1e6),
-                   "preroll_steps": args.preroll, "mean_rk_attempts": mean_att},
-        "gpu_launches": K * (2 if env.scratch is not None else 1),
+                   "preroll_steps": args.preroll, "mean_rk_attempts": mean_att,
+                   "stream_lanes": env.lanes,
+                   "streams": (f"each step runs as {env.lanes} contiguous env sub-ranges on {env.lanes} CUDA streams "
+                               "(r6_step_range), forked from and joined back into the timed stream around the K steps"
+                               if env.lanes > 1 else "one stream")},
+        "gpu_launches": K * (2 if env.scratch is not None else 1) * env.lanes,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
                      "frac": ach_tf / peaks["fp64"], "traffic": traffic, "traffic_unit": "B/launch",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_STEP * n,
                      "note": "algorithmic flops/env-step = 985 + 1850 x RK attempts (SURVEY 8d) x envs per launch; "
                              "peak = DFMA micro-benchmark measured in this run (r6_peak_fma)",
                      "flops_per_env_step": flops_step,
-                     "kernel": "integrate_kernel + post_kernel (r6_step as two launches)" if env.scratch is not None else "step_kernel",
+                     "kernel": (f"integrate_kernel + post_kernel (r6_step as two launches per lane, {env.lanes} lane(s)); "
+                                "launch_ms = the whole env-step") if env.scratch is not None else "step_kernel",
                      "launch_ms": ms_step},
+        "step_joined_every_step": {"value": world * n * K / (ms_joined * 1e-3), "unit": UNIT, "ms_per_step": ms_joined / K,
+                                   "what": "same K steps with the lanes joined into the caller's stream after every step "
+                                           "(outputs consumable on that stream per step)"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gb / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_STEP},

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 13
+#define R6_ABI_VERSION 14
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -191,6 +191,17 @@ int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env
                    int64_t step_index, void *stream);
 
 /*
+ * r6_step / r6_step_random restricted to the env sub-range [first, first + count) of the batch; n stays the size
+ * (= SoA stride) of the buffers and actions the full [n][3] array (NULL: Philox actions keyed by step_index, as
+ * r6_step_random).  Envs are independent (rocket_env.py:201-231 touches one env), so a host may step disjoint
+ * sub-ranges of one batch on different streams: the tail of one range's kernels then overlaps the next range's
+ * work instead of idling the SMs.  Needs R6Buffers.scratch (kernel pair only).  Ordering between the streams and
+ * whatever consumes the outputs is the caller's business.
+ */
+int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count,
+                  int64_t env_offset, const float *actions, uint64_t seed, int64_t step_index, void *stream);
+
+/*
  * k fused env-steps per launch with the state held in registers.
  * mode R6_ACT_PHILOX: action = uniform(-1,1) from (seed, global env id, step_base + j);
  * mode R6_ACT_MLP:    action = clip(actor(obs[0:13]), -1, 1), the deterministic SB3 MlpPolicy forward
@@ -244,6 +255,15 @@ int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_core
 int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, int32_t stochastic, uint64_t seed,
                  int64_t env_offset, int64_t step_index, float *actions, float *actions_raw, float *values,
                  float *log_prob, void *stream);
+
+/*
+ * r6_policy_ex for the env sub-range [first, first + count): obs stays the [14][n] array (n = its stride) and the
+ * outputs the full [n]-sized arrays, of which only the rows of the sub-range are written.  Pairs with
+ * r6_step_range so that a closed loop (policy, env step) can run per sub-range on its own stream.
+ */
+int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first, int64_t count, int32_t tensor_cores,
+                    int32_t stochastic, uint64_t seed, int64_t env_offset, int64_t step_index, float *actions,
+                    float *actions_raw, float *values, float *log_prob, void *stream);
 
 /*
  * Generalised advantage estimation over a recorded rollout, on the device, so that the PPO update of

@@ -35,7 +35,7 @@ class Rocket6DOFBatch:
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
                  ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
                  precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None,
-                 split_step: Optional[bool] = None):
+                 split_step: Optional[bool] = None, lanes: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -83,6 +83,20 @@ class Rocket6DOFBatch:
             if split_step is None:
                 env_flag = os.environ.get("R6_SPLIT_STEP")
                 split_step = (n > SPLIT_MIN_ENVS) if env_flag is None else (env_flag != "0")
+            # stream lanes: `step` / `step_random` run the kernel pair on `lanes` contiguous env sub-ranges, each on
+            # its own stream, so one range's kernel tails (the integrator grid is ~18 waves of one-warp CTAs of
+            # uneven length) are covered by the next range's work: 0.468 -> 0.430 ms per 2^20-env step free-running,
+            # 0.454 ms when every step is joined back into the caller's stream (profiles/two_stream_shards.py)
+            self.lanes = max(int(lanes), 1)
+            if self.lanes > 1:
+                if n < self.lanes:
+                    raise ValueError("more lanes than envs")
+                split_step = True
+                self._lane_streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
+                base, rem = divmod(n, self.lanes)
+                self._lane_ranges = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(self.lanes)]
+                self._lane_fork = torch.cuda.Event()
+            self._lanes_pending = False
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
             self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
@@ -117,6 +131,38 @@ class Rocket6DOFBatch:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # ------------------------------------------------------------------ stream lanes
+    def _step_lanes(self, actions: Optional[torch.Tensor], k: int, join: bool):
+        """k env-steps over the lanes: every lane stream first waits for what the caller's stream has enqueued so far
+        (the producer of `actions`, the previous joined step), then runs its sub-range's kernel pairs back to back."""
+        cur = torch.cuda.current_stream(self.device)
+        self._lane_fork.record(cur)
+        ap = 0 if actions is None else actions.data_ptr()
+        with torch.cuda.device(self.device):
+            for st in self._lane_streams:
+                st.wait_event(self._lane_fork)
+                if actions is not None:
+                    actions.record_stream(st)
+            for j in range(int(k)):
+                for (first, count), st in zip(self._lane_ranges, self._lane_streams):
+                    _lib.check(self.lib.r6_step_range(C.byref(self._p), C.byref(self._b), self.num_envs, first, count,
+                                                      self.env_offset, ap, self.seed_value, self.steps_done + j,
+                                                      st.cuda_stream), self.lib)
+        self.steps_done += int(k)
+        self._lanes_pending = True
+        if join:
+            self.join()
+
+    def join(self):
+        """Orders everything the lanes have been given before whatever the caller's current stream does next.  A no-op
+        without lanes or when nothing is pending; every method other than `step(..., join=False)` /
+        `step_random(..., join=False)` joins by itself."""
+        if self._lanes_pending:
+            cur = torch.cuda.current_stream(self.device)
+            for st in self._lane_streams:
+                cur.wait_stream(st)
+            self._lanes_pending = False
+
     # ------------------------------------------------------------------ gym-like API (batched)
     def seed(self, seed: int):
         self.seed_value = int(seed)
@@ -124,6 +170,7 @@ class Rocket6DOFBatch:
 
     def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Rocket6DOF.reset for every env (or those with mask != 0). Returns obs [14, N] (view)."""
+        self.join()
         mp = 0
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -133,12 +180,17 @@ class Rocket6DOFBatch:
                                          self.seed_value, self._stream()), self.lib)
         return self.obs
 
-    def step(self, actions: torch.Tensor):
+    def step(self, actions: torch.Tensor, *, join: bool = True):
         """actions: float32 CUDA tensor [N, 3] in [-1, 1].  Returns (obs[14,N], reward[N], done[N], flags[N])
-        as views of the persistent output tensors (valid until the next call)."""
+        as views of the persistent output tensors (valid until the next call).  With stream lanes, join=False leaves
+        the step running on the lane streams (the outputs are ordered on the caller's stream only after `join()`), so
+        consecutive steps pipeline; the default joins every step."""
         if actions.dtype != torch.float32 or not actions.is_cuda or actions.shape != (self.num_envs, 3):
             raise ValueError("actions must be a float32 CUDA tensor of shape [num_envs, 3]")
         actions = actions.contiguous()
+        if self.lanes > 1:
+            self._step_lanes(actions, 1, join)
+            return self.obs, self.reward, self.done, self.flags
         with torch.cuda.device(self.device):
             _lib.check(self.lib.r6_step(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset,
                                         actions.data_ptr(), self.seed_value, self._stream()), self.lib)
@@ -151,6 +203,7 @@ class Rocket6DOFBatch:
         (`r6_rollout`).  For the random policy on large auto-reset batches the integrator | post-step kernel pair
         is faster than the fused kernel, so fused=None picks `step_random` there (same action stream, results equal to
         round-off); recording, other action sources and one-episode semantics always use the fused kernel."""
+        self.join()
         if fused is None:
             fused = not (mode == ACT_PHILOX and not record and self.auto_reset and self.num_envs > SPLIT_MIN_ENVS)
         if not fused:
@@ -186,13 +239,16 @@ class Rocket6DOFBatch:
         self.steps_done += int(k)
         return traj
 
-    def step_random(self, k: int = 1):
+    def step_random(self, k: int = 1, *, join: bool = True):
         """k env-steps with in-kernel Philox actions through the integrator | post-step kernel pair (2k launches).
         Same action stream and results as `rollout(k)`; faster for large batches, where the two specialised kernels
-        beat the single fused one."""
+        beat the single fused one.  With stream lanes the k steps run free on the lanes and are joined at the end."""
         if self.scratch is None:                       # the random-action step exists only as the kernel pair
             self.scratch = torch.zeros(2, self.num_envs, dtype=torch.uint8, device=self.device)
             self._b.scratch = self.scratch.data_ptr()
+        if self.lanes > 1:
+            self._step_lanes(None, k, join)
+            return self.obs, self.reward, self.done, self.flags
         with torch.cuda.device(self.device):
             for _ in range(int(k)):
                 _lib.check(self.lib.r6_step_random(C.byref(self._p), C.byref(self._b), self.num_envs, self.env_offset,
@@ -204,6 +260,7 @@ class Rocket6DOFBatch:
         """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch).
         tensor_cores: False / 0 = float32 FMA network; True / 1 = mma.sync 3xTF32 tiles (faithful to 2e-6);
         2 = tcgen05 + TMEM single-pass TF32 (fast mode, ~1e-3)."""
+        self.join()
         if out is None:
             out = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
         m = _lib.make_mlp(mlp)
@@ -218,6 +275,7 @@ class Rocket6DOFBatch:
         (env_actions [N,3] clipped, raw_actions [N,3], values [N], log_prob [N]).  `mlp` may carry the critic head
         ("wv", "bv") and the Gaussian "log_std"; stochastic=True samples mean + exp(log_std) eps with Philox noise
         keyed by (seed, global env id, step_index) — reproducible and independent of the shard count."""
+        self.join()
         n, dev = self.num_envs, self.device
         if out is not None:                      # (act, raw, val, logp) contiguous float32 CUDA tensors to write into
             act, raw, val, logp = out
@@ -260,13 +318,35 @@ class Rocket6DOFBatch:
         return dict(obs=obs, actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones, advantages=adv,
                     returns=ret, last_values=last_v)
 
-    def step_policy(self, k: int, mlp: dict, *, tensor_cores=False):
+    def step_policy(self, k: int, mlp: dict, *, tensor_cores=False, join: bool = True):
         """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes
         the actions, the step kernel consumes them — VecEnv semantics (auto-reset as configured).  Faster than the
-        single fused rollout kernel for large batches; `rollout(k, ACT_MLP)` remains for one-episode semantics."""
+        single fused rollout kernel for large batches; `rollout(k, ACT_MLP)` remains for one-episode semantics.
+        With stream lanes every lane runs its own policy -> step chain (r6_policy_range, r6_step_range) for the k
+        steps and the lanes are joined at the end."""
         act = getattr(self, "_policy_act", None)
         if act is None:
             act = self._policy_act = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
+        if self.lanes > 1:
+            m = _lib.make_mlp(mlp)
+            cur = torch.cuda.current_stream(self.device)
+            self._lane_fork.record(cur)
+            n, L = self.num_envs, self.lib
+            with torch.cuda.device(self.device):
+                for st in self._lane_streams:
+                    st.wait_event(self._lane_fork)
+                for j in range(int(k)):
+                    for (first, count), st in zip(self._lane_ranges, self._lane_streams):
+                        _lib.check(L.r6_policy_range(C.byref(m), self.obs.data_ptr(), n, first, count, int(tensor_cores), 0,
+                                                     self.seed_value, self.env_offset, self.steps_done + j, act.data_ptr(),
+                                                     None, None, None, st.cuda_stream), L)
+                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, self.env_offset,
+                                                   act.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
+            self.steps_done += int(k)
+            self._lanes_pending = True
+            if join:
+                self.join()
+            return self.obs, self.reward, self.done, self.flags
         for _ in range(int(k)):
             self.policy_actions(mlp, tensor_cores=tensor_cores, out=act)
             self.step(act)
@@ -276,6 +356,7 @@ class Rocket6DOFBatch:
     def set_state(self, state: torch.Tensor, idx: Optional[torch.Tensor] = None, *, step_count: int = 0):
         """Starts new episodes from given float32 initial conditions [M,14] (already normalised
         quaternion), as `reset()` would after sampling them (parity runs inject the oracle's ICs)."""
+        self.join()
         ic = torch.as_tensor(state, dtype=torch.float32, device=self.device).reshape(-1, 14)
         if idx is None:
             idx = torch.arange(self.num_envs, device=self.device)
@@ -294,10 +375,12 @@ class Rocket6DOFBatch:
         return self.state
 
     def reset_stats(self):
+        self.join()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.r6_stats_reset(self.stats.data_ptr(), self._stream()), self.lib)
 
     def stats_dict(self, stats: Optional[torch.Tensor] = None) -> dict:
+        self.join()
         s = (self.stats if stats is None else stats).detach().cpu().numpy()
         d = dict(zip(STAT_NAMES, (float(x) for x in s)))
         ep = max(d["episodes"], 1.0)

@@ -254,13 +254,13 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 template <class R, bool kExact>
 __global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
 integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
-                 uint64_t seed, int64_t step_index)
+                 uint64_t seed, int64_t step_index, int64_t i0, int64_t i1)
 {
-    const int64_t i = (int64_t)blockIdx.x * kIntThreads + threadIdx.x;
+    const int64_t i = i0 + (int64_t)blockIdx.x * kIntThreads + threadIdx.x;     // this launch steps envs [i0, i1)
     extern __shared__ double r6_smem[];
     KShared<R, kIntThreads> K;
     K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
-    if (i >= n) return;
+    if (i >= i1) return;
     R *state = reinterpret_cast<R *>(b.state);
     R y[14];
 #pragma unroll
@@ -282,10 +282,10 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
 template <class R>
 __global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
 post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
-            const float *__restrict__ actions, uint64_t seed, int64_t step_index)
+            const float *__restrict__ actions, uint64_t seed, int64_t step_index, int64_t i0, int64_t i1)
 {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) {
+    const int64_t i = i0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < i1) {
         EnvT<R> e;
         env_load(b, n, i, e);
         float a0, a1, a2;
@@ -321,7 +321,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
             b.ep_return[i] = e.ep_return;
         }
     }
-    if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
+    if (b.stats) stats_steps(b.stats, i < i1 ? 1 : 0);
 }
 
 // k fused steps, state in registers; actions from Philox, a [k][n][3] buffer or the fused policy MLP.
@@ -510,6 +510,7 @@ struct PolicyOut {
     int stochastic;
     uint64_t seed;
     int64_t env_offset, step;
+    int64_t i0, i1;                           // env sub-range of this launch (r6_policy_range); n stays the obs stride
 };
 __device__ __forceinline__ void policy_epilogue(const PolicyOut &po, const float *log_std, int64_t i, const float (&out)[4])
 {
@@ -536,15 +537,16 @@ policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const P
     const int nW = kTc ? kMlpTcFloats : kMlpFloats;
     for (int idx = threadIdx.x; idx < nW; idx += kThreads) Ws[idx] = kTc ? mlp_tc_pack_element(mlp, idx) : mlp_pack_element(mlp, idx);
     __syncthreads();
-    const int64_t tiles = (n + kThreads - 1) / kThreads;
+    const int64_t i1 = po.i1;
+    const int64_t tiles = (i1 - po.i0 + kThreads - 1) / kThreads;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t i = tile * kThreads + threadIdx.x;
+        const int64_t i = po.i0 + tile * kThreads + threadIdx.x;
         float x[kMlpIn], out[4];
 #pragma unroll
-        for (int c = 0; c < kMlpIn; c++) x[c] = i < n ? obs[(int64_t)c * n + i] : 0.0f;
+        for (int c = 0; c < kMlpIn; c++) x[c] = i < i1 ? obs[(int64_t)c * n + i] : 0.0f;
         if (kTc) mlp_forward_tc(Ws, Ws + kMlpTcFloats + (threadIdx.x >> 5) * (16 * 33), x, out);
         else mlp_forward(Ws, x, out);
-        if (i < n) policy_epilogue(po, mlp.log_std, i, out);
+        if (i < i1) policy_epilogue(po, mlp.log_std, i, out);
     }
 }
 constexpr int kSmemPolicyTc = (r6::kMlpTcFloats + (kThreads / 32) * 16 * 33) * (int)sizeof(float);
@@ -593,17 +595,18 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, con
     const uint32_t aX = smem_u32(S + kOffX), aH = smem_u32(S + kOffH);
     const uint32_t aW0 = smem_u32(S + kOffW0), aW1 = smem_u32(S + kOffW1), aW2 = smem_u32(S + kOffW2);
     uint32_t phase = 0;
-    const int64_t tiles = (n + kTile - 1) / kTile;
+    const int64_t i1 = po.i1;
+    const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + tid;
+        const int64_t i = po.i0 + tile * kTile + tid;
         // ---- observations of this thread's env -> row `tid` of the X tile ----
 #pragma unroll
         for (int kc = 0; kc < 4; kc++) {
             float4 v;
-            v.x = (4 * kc + 0 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 0) * n + i]) : 0.0f;
-            v.y = (4 * kc + 1 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 1) * n + i]) : 0.0f;
-            v.z = (4 * kc + 2 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 2) * n + i]) : 0.0f;
-            v.w = (4 * kc + 3 < kMlpIn && i < n) ? round_tf32(obs[(int64_t)(4 * kc + 3) * n + i]) : 0.0f;
+            v.x = (4 * kc + 0 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 0) * n + i]) : 0.0f;
+            v.y = (4 * kc + 1 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 1) * n + i]) : 0.0f;
+            v.z = (4 * kc + 2 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 2) * n + i]) : 0.0f;
+            v.w = (4 * kc + 3 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 3) * n + i]) : 0.0f;
             *reinterpret_cast<float4 *>(S + kOffX + tile_off(tid, 4 * kc, 16)) = v;
         }
         fence_async_smem(); fence_before(); __syncthreads();
@@ -627,7 +630,7 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, con
         {
             float v[32];
             tmem_ld32(tmem_row + kColD2, v);
-            if (i < n) {
+            if (i < i1) {
                 const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
                 policy_epilogue(po, mlp.log_std, i, out);
             }
@@ -743,17 +746,22 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
 
 template <class R>
 void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset,
-                 const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0)
+                 const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0, int64_t first = 0,
+                 int64_t count = -1)
 {
-    const unsigned g = (unsigned)blocks_for(n);
-    if (b->scratch != nullptr) {
-        const unsigned gi = (unsigned)((n + kIntThreads - 1) / kIntThreads);
+    if (b->scratch != nullptr) {                 // kernel pair over the env sub-range [first, first + count)
+        if (count < 0) count = n;
+        const unsigned gi = (unsigned)((count + kIntThreads - 1) / kIntThreads);
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
-        if (p->dt <= kMaxDtSeries) integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
-        else integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index);
-        post_kernel<R><<<g, kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index);
+        if (p->dt <= kMaxDtSeries)
+            integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, first + count);
+        else
+            integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, first + count);
+        post_kernel<R><<<(unsigned)blocks_for(count), kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first,
+                                                                      first + count);
         return;
     }
+    const unsigned g = (unsigned)blocks_for(n);
     if (p->dt <= kMaxDtSeries) step_kernel<R, false><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
     else step_kernel<R, true><<<g, kThreads, smem_bytes<R>(), s>>>(*p, *b, dv, n, env_offset, actions, seed);
 }
@@ -839,6 +847,23 @@ int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env
     return check_launch("r6_step_random");
 }
 
+int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count, int64_t env_offset,
+                  const float *actions, uint64_t seed, int64_t step_index, void *stream)
+{
+    int rc = validate_step(p, b, n);
+    if (rc) return rc;
+    if (!b->scratch) return fail(R6_EINVAL, "r6_step_range needs R6Buffers.scratch%s");
+    if (first < 0 || count < 0 || first + count > n) return fail(R6_EINVAL, "env sub-range outside [0, n)%s");
+    if (count == 0) return R6_OK;
+    if ((rc = ensure_attributes())) return rc;
+    const Derived dv = make_derived(*p);
+    if (p->precision == R6_PREC_F32)
+        launch_step<float>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count);
+    else
+        launch_step<double>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count);
+    return check_launch("r6_step_range");
+}
+
 int r6_rollout(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env_offset, int32_t k, int32_t mode,
                const R6Mlp *mlp, const float *act_buf, uint64_t seed, int64_t step_base, float *traj_obs,
                float *traj_act, float *traj_rew, uint8_t *traj_done, void *stream)
@@ -881,16 +906,17 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
     return check_launch("r6_tgo");
 }
 
-int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, int32_t stochastic, uint64_t seed,
-                 int64_t env_offset, int64_t step_index, float *actions, float *actions_raw, float *values,
-                 float *log_prob, void *stream)
+int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first, int64_t count, int32_t tensor_cores,
+                    int32_t stochastic, uint64_t seed, int64_t env_offset, int64_t step_index, float *actions,
+                    float *actions_raw, float *values, float *log_prob, void *stream)
 {
     if (!mlp || !mlp->w0 || !mlp->b0 || !mlp->w1 || !mlp->b1 || !mlp->w2 || !mlp->b2)
         return fail(R6_EINVAL, "policy weights are null%s");
     if (!obs || !actions) return fail(R6_EINVAL, "null pointer%s");
     if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    if (first < 0 || count < 0 || first + count > n) return fail(R6_EINVAL, "env sub-range outside [0, n)%s");
     if (tensor_cores < 0 || tensor_cores > 2) return fail(R6_EINVAL, "tensor_cores must be 0, 1 or 2%s");
-    if (n == 0) return R6_OK;
+    if (count == 0) return R6_OK;
     int rc = ensure_attributes();
     if (rc) return rc;
     // one resident wave: SM count x resident CTAs per SM
@@ -900,13 +926,22 @@ int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_c
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
-    const PolicyOut po = {actions, actions_raw, values, log_prob, stochastic, seed, env_offset, step_index};
+    const PolicyOut po = {actions, actions_raw, values, log_prob, stochastic, seed, env_offset, step_index, first, first + count};
     const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
-    const unsigned g = (unsigned)(blocks_for(n) < wave ? blocks_for(n) : wave);
+    const unsigned g = (unsigned)(blocks_for(count) < wave ? blocks_for(count) : wave);
     if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     return check_launch("r6_policy");
+}
+
+int r6_policy_ex(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, int32_t stochastic, uint64_t seed,
+                 int64_t env_offset, int64_t step_index, float *actions, float *actions_raw, float *values,
+                 float *log_prob, void *stream)
+{
+    if (n < 0) return fail(R6_EINVAL, "n < 0%s");
+    return r6_policy_range(mlp, obs, n, 0, n, tensor_cores, stochastic, seed, env_offset, step_index, actions, actions_raw,
+                           values, log_prob, stream);
 }
 
 int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream)

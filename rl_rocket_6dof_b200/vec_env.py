@@ -98,6 +98,7 @@ class Rocket6DOFVecEnv:
         b = self.batch
         a = torch.as_tensor(actions, dtype=torch.float32).reshape(self.num_envs, 3)
         if self.zero_copy:
+            b.join()
             if not (a.is_pinned() and a.is_contiguous()):
                 self._act_h.copy_(a)
                 a = self._act_h
