@@ -308,11 +308,36 @@ class Rocket6DOFBatch:
         rews = torch.empty(k, n, dtype=torch.float32, device=dev)
         dones = torch.empty(k, n, dtype=torch.uint8, device=dev)
         a_env = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        for j in range(int(k)):
-            obs[j] = self.obs[:13].t()
-            self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores, out=(a_env, acts[j], vals[j], logp[j]))
-            self.step(a_env)
-            rews[j], dones[j] = self.reward_f32, self.done
+        if self.lanes > 1:
+            # every lane records its own rows: [obs copy, policy, env step, reward / done copies] x k on its stream
+            self.join()
+            m = _lib.make_mlp(mlp)
+            L = self.lib
+            self._lane_fork.record(torch.cuda.current_stream(dev))
+            for st in self._lane_streams:
+                st.wait_event(self._lane_fork)
+            for j in range(int(k)):
+                for (first, count), st in zip(self._lane_ranges, self._lane_streams):
+                    sl = slice(first, first + count)
+                    with torch.cuda.stream(st):
+                        obs[j, sl] = self.obs[:13, sl].t()
+                        _lib.check(L.r6_policy_range(C.byref(m), self.obs.data_ptr(), n, first, count, int(tensor_cores),
+                                                     int(bool(stochastic)), self.seed_value, self.env_offset,
+                                                     self.steps_done + j, a_env.data_ptr(), acts[j].data_ptr(),
+                                                     vals[j].data_ptr(), logp[j].data_ptr(), st.cuda_stream), L)
+                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, self.env_offset,
+                                                   a_env.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
+                        rews[j, sl] = self.reward_f32[sl]
+                        dones[j, sl] = self.done[sl]
+            self.steps_done += int(k)
+            self._lanes_pending = True
+            self.join()
+        else:
+            for j in range(int(k)):
+                obs[j] = self.obs[:13].t()
+                self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores, out=(a_env, acts[j], vals[j], logp[j]))
+                self.step(a_env)
+                rews[j], dones[j] = self.reward_f32, self.done
         _, _, last_v, _ = self.policy_forward(mlp, stochastic=False, tensor_cores=tensor_cores)
         adv, ret = compute_gae(rews, vals, dones, last_v, gamma, gae_lambda)
         return dict(obs=obs, actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones, advantages=adv,

@@ -112,3 +112,23 @@ def test_closed_loop_on_lanes(tc):
     import torch
     assert torch.equal(one._policy_act, many._policy_act)
     assert float(one.stats[0]) > 0
+
+
+def test_collect_rollout_on_lanes():
+    """PPO rollout collection per lane == single stream (stochastic policy: Philox noise keyed by global env id)."""
+    import torch
+    from rl_rocket_6dof_b200 import policy as pol
+    rng = np.random.default_rng(5)
+    w = {k: (rng.standard_normal(shp) * 0.2).astype(np.float32) for k, shp in pol.SHAPES.items()}
+    w.update(wv=(rng.standard_normal(64) * 0.3).astype(np.float32), bv=np.zeros(1, np.float32),
+             log_std=np.array([-1.0, -1.5, -2.0], np.float32))
+    n, k = 2051, 48
+    one, many = _mk(n, 1), _mk(n, 2)
+    wd = {key: torch.from_numpy(v).cuda() for key, v in w.items()}
+    one.reset(); many.reset()
+    a = one.collect_rollout(k, wd)
+    b = many.collect_rollout(k, wd)
+    torch.cuda.synchronize()
+    for key in a:
+        assert torch.equal(a[key], b[key]), key
+    _same(one, many)
