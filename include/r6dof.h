@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 14
+#define R6_ABI_VERSION 15
+#define R6_MAX_LANES 32
 #define R6_NSTATE 14
 #define R6_NTERMS 7
 #define R6_NSTATS 8
@@ -147,6 +148,10 @@ typedef struct R6Buffers {
     double *stats;          /* [8] nullable: R6_S_* accumulators */
     uint8_t *scratch;       /* [2][n] nullable DEVICE bytes: when given, r6_step runs as two kernels (integrator | reward,
                                flags, reset, observation) that hand the solver status / attempt count through it */
+    uint8_t *work;          /* nullable, needs scratch: r6_work_bytes(n) DEVICE bytes, zero-filled once by the caller.
+                               When given, the integrator runs as three passes cut at RK-attempt boundaries, the
+                               unfinished envs of a pass compacted into work lists for the next (a warp then never
+                               idles through attempts only some of its envs need) */
 } R6Buffers;
 
 /* Weights of the SB3 MlpPolicy actor (net_arch [128, 64], tanh), float32 row-major [out][in]. */
@@ -196,10 +201,14 @@ int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env
  * r6_step_random).  Envs are independent (rocket_env.py:201-231 touches one env), so a host may step disjoint
  * sub-ranges of one batch on different streams: the tail of one range's kernels then overlaps the next range's
  * work instead of idling the SMs.  Needs R6Buffers.scratch (kernel pair only).  Ordering between the streams and
- * whatever consumes the outputs is the caller's business.
+ * whatever consumes the outputs is the caller's business.  lane (0 .. R6_MAX_LANES-1) names the caller's stream:
+ * ranges that may run concurrently must use different lanes (each lane has its own work-list counters).
  */
-int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count,
+int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count, int32_t lane,
                   int64_t env_offset, const float *actions, uint64_t seed, int64_t step_index, void *stream);
+
+/* Size of R6Buffers.work for n envs. */
+int64_t r6_work_bytes(int64_t n);
 
 /*
  * k fused env-steps per launch with the state held in registers.

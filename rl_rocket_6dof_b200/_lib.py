@@ -12,7 +12,7 @@ from .params import R6Params
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libr6dof.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 u8p = C.c_void_p
 
@@ -30,6 +30,7 @@ class R6Buffers(C.Structure):
         ("ic_table_len", C.c_int64), ("n_global", C.c_int64),
         ("stats", C.c_void_p),
         ("scratch", C.c_void_p),
+        ("work", C.c_void_p),
     ]
 
 
@@ -51,7 +52,7 @@ def make_mlp(weights: dict) -> "R6Mlp":
 
 
 EXPORTS = ["r6_abi_version", "r6_last_error", "r6_params_size", "r6_buffers_size", "r6_reset", "r6_step",
-           "r6_rollout", "r6_sim_step_raw", "r6_tgo", "r6_stats_reset", "r6_peak_fma", "r6_gae", "r6_policy", "r6_policy_ex", "r6_step_random", "r6_step_range", "r6_policy_range"]
+           "r6_rollout", "r6_sim_step_raw", "r6_tgo", "r6_stats_reset", "r6_peak_fma", "r6_gae", "r6_policy", "r6_policy_ex", "r6_step_random", "r6_step_range", "r6_policy_range", "r6_work_bytes"]
 
 
 class R6Error(RuntimeError):
@@ -95,7 +96,10 @@ def load(path: str | None = None):
     L.r6_tgo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]
     L.r6_stats_reset.argtypes = [C.c_void_p, C.c_void_p]
     L.r6_step_random.argtypes = [pp, bp, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p]
-    L.r6_step_range.argtypes = [pp, bp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]
+    L.r6_step_range.argtypes = [pp, bp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_uint64, C.c_int64,
+                                C.c_void_p]
+    L.r6_work_bytes.argtypes = [C.c_int64]
+    L.r6_work_bytes.restype = C.c_int64
     L.r6_policy_range.argtypes = [C.POINTER(R6Mlp), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.r6_policy_ex.argtypes = [C.POINTER(R6Mlp), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int64,

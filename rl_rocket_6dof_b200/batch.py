@@ -35,7 +35,7 @@ class Rocket6DOFBatch:
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
                  ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
                  precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None,
-                 split_step: Optional[bool] = None, lanes: int = 1):
+                 split_step: Optional[bool] = None, lanes: int = 1, multipass: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -98,6 +98,15 @@ class Rocket6DOFBatch:
                 self._lane_fork = torch.cuda.Event()
             self._lanes_pending = False
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
+            # multi-pass integrator (R6Buffers.work): one RK attempt per pass, unfinished envs compacted into work
+            # lists for the next pass; on with the float64 kernel pair unless asked otherwise (+4.4 % there; the
+            # float32 integrator is issue-bound and loses 1.5 % to the extra passes)
+            if multipass is None:
+                env_flag = os.environ.get("R6_MULTIPASS")
+                multipass = (split_step and precision == "fp64") if env_flag is None else (env_flag != "0" and split_step)
+            if multipass and not split_step:
+                raise ValueError("multipass needs the split step (split_step=True)")
+            self.work = torch.zeros(int(self.lib.r6_work_bytes(n)), dtype=torch.uint8, device=dev) if multipass else None
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
             self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
             self.nattempts = torch.zeros(n, dtype=torch.uint8, device=dev) if (debug_buffers or record_attempts) else None
@@ -126,6 +135,7 @@ class Rocket6DOFBatch:
         b.n_global = self.num_envs_global
         b.stats = ptr(self.stats)
         b.scratch = ptr(self.scratch)
+        b.work = ptr(self.work)
         return b
 
     def _stream(self) -> int:
@@ -144,8 +154,8 @@ class Rocket6DOFBatch:
                 if actions is not None:
                     actions.record_stream(st)
             for j in range(int(k)):
-                for (first, count), st in zip(self._lane_ranges, self._lane_streams):
-                    _lib.check(self.lib.r6_step_range(C.byref(self._p), C.byref(self._b), self.num_envs, first, count,
+                for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
+                    _lib.check(self.lib.r6_step_range(C.byref(self._p), C.byref(self._b), self.num_envs, first, count, ln,
                                                       self.env_offset, ap, self.seed_value, self.steps_done + j,
                                                       st.cuda_stream), self.lib)
         self.steps_done += int(k)
@@ -317,7 +327,7 @@ class Rocket6DOFBatch:
             for st in self._lane_streams:
                 st.wait_event(self._lane_fork)
             for j in range(int(k)):
-                for (first, count), st in zip(self._lane_ranges, self._lane_streams):
+                for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
                     sl = slice(first, first + count)
                     with torch.cuda.stream(st):
                         obs[j, sl] = self.obs[:13, sl].t()
@@ -325,7 +335,7 @@ class Rocket6DOFBatch:
                                                      int(bool(stochastic)), self.seed_value, self.env_offset,
                                                      self.steps_done + j, a_env.data_ptr(), acts[j].data_ptr(),
                                                      vals[j].data_ptr(), logp[j].data_ptr(), st.cuda_stream), L)
-                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, self.env_offset,
+                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, ln, self.env_offset,
                                                    a_env.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
                         rews[j, sl] = self.reward_f32[sl]
                         dones[j, sl] = self.done[sl]
@@ -361,11 +371,11 @@ class Rocket6DOFBatch:
                 for st in self._lane_streams:
                     st.wait_event(self._lane_fork)
                 for j in range(int(k)):
-                    for (first, count), st in zip(self._lane_ranges, self._lane_streams):
+                    for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
                         _lib.check(L.r6_policy_range(C.byref(m), self.obs.data_ptr(), n, first, count, int(tensor_cores), 0,
                                                      self.seed_value, self.env_offset, self.steps_done + j, act.data_ptr(),
                                                      None, None, None, st.cuda_stream), L)
-                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, self.env_offset,
+                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, ln, self.env_offset,
                                                    act.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
             self.steps_done += int(k)
             self._lanes_pending = True

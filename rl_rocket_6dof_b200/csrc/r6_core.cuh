@@ -648,8 +648,21 @@ R6_HD float inv_root5(float x)
 // evaluation point is always  y + h * sum_j SA[row][j] K_j  (rows of the extended tableau above), built
 // by one rolled loop.  This keeps the hot instruction footprint to a few KB (the instruction cache is
 // what the unrolled formulation was bound by) at the price of a switch per evaluation.
-template <bool kExact, class KS, class R>
-R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
+//
+// kPass (multi-pass integration, integrate_pass_kernel): the adaptive step count differs per env (1 attempt for a
+// third of them, 2 for most, 3-4 rarely) and a warp pays for its slowest lane, so the step can also be cut at
+// attempt boundaries: kPass = 1 starts normally and returns -2 ("unfinished") after px->budget attempts with the
+// solver's private state in *px; kPass = 2 resumes from *px.  Only (t, h_abs, rejected, natt) and the height the
+// density expansion was set up at are carried: f(y), the first-same-as-last stage, is re-evaluated from the stored y
+// (same inputs, same instructions => the same bits).  kPass = 0 is the single-call form.
+template <class R>
+struct PassCtx {
+    R t, h_abs, h_ref;
+    int natt, budget;
+    bool rejected;
+};
+template <bool kExact, class KS, class R, int kPass = 0>
+R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx<R> *px = nullptr)
 {
     const TabT<R> &T = tab<R>();
     constexpr R rtol = R(1e-3), atol = R(1e-6);
@@ -658,7 +671,8 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
     const R t_bound = t + dt;
     const R L = fabs(t_bound - t);                       // common.py:100 (interval length as SciPy computes it)
     const R w0 = y[10];
-    density_setup(c, y[0]);
+    if constexpr (kPass == 2) density_setup(c, px->h_ref);
+    else density_setup(c, y[0]);
     // evaluation point (height, v, q, w1, w2, m) + the two horizontal positions of y_new
     R xh = y[0], xv0 = y[3], xv1 = y[4], xv2 = y[5], xq0 = y[6], xq1 = y[7], xq2 = y[8], xq3 = y[9];
     R xw1 = y[11], xw2 = y[12], xm = y[13], xr1 = y[1], xr2 = y[2];
@@ -668,6 +682,10 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
     int status = -2;
     bool rejected = false;
     natt = 0;
+    int budget = 0;
+    if constexpr (kPass != 0) budget = px->budget;
+    if constexpr (kPass == 1) px->h_ref = y[0];
+    if constexpr (kPass == 2) { t = px->t; t_new = t; h_abs = px->h_abs; rejected = px->rejected; natt = px->natt; }
     for (;;) {
         const DerivT<R> d = rhs<kExact>(c, w0, xh, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2, xm);
         bool begin_attempt = false;
@@ -734,6 +752,15 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
                 h_abs *= fmax(R(0.2), raw);
                 rejected = true;
             }
+            if constexpr (kPass != 0) {
+                if (--budget == 0) {                                // hand the env to the next pass
+                    px->t = t; px->h_abs = h_abs; px->rejected = rejected; px->natt = natt;
+                    break;
+                }
+            }
+            begin_attempt = true;
+        } else if (kPass == 2 && stage == kStageF0) {
+            k_store(K, 0, d);                                       // f(y) again: the first-same-as-last stage
             begin_attempt = true;
         } else if (stage == kStageF0) {
             // ---- d = f0 (rk.py:96); select_initial_step part 1 (common.py:105-119), order 4 ----
@@ -1436,6 +1463,25 @@ R6_HD void env_integrate(const R6Params &p, const double *__restrict__ t_table, 
     }
     status = integrate<kExact>(c, y, t, (R)p.dt, natt, K);
     normalize_quat(y);
+}
+
+// env_integrate cut at attempt boundaries (see integrate<..., kPass>): returns -2 while the env is unfinished.
+template <bool kExact, int kPass, class KS, class R>
+R6_HD int env_integrate_pass(const R6Params &p, const double *__restrict__ t_table, R *y, float m0, int k, float a0,
+                             float a1, float a2, KS &K, PassCtx<R> &px, int &natt)
+{
+    float u0, u1, u2;
+    denormalize_action(p, a0, a1, a2, u0, u1, u2);
+    StepConstT<R> c;
+    consts_env_mode(c, m0, u0, u1, u2, y[10]);
+    R t = 0;
+    if constexpr (sizeof(R) == 8) {
+        const int kk = k < p.n_t ? k : p.n_t - 1;
+        t = (R)t_table[kk];
+    }
+    const int status = integrate<kExact, KS, R, kPass>(c, y, t, (R)p.dt, natt, K, &px);
+    if (status != -2) normalize_quat(y);
+    return status;
 }
 
 // Second half: rocket_env.py:206-231 on the post-step state + the make_env() / reward wrappers.  e.k is the step

@@ -276,15 +276,139 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
     b.scratch[n + i] = (uint8_t)natt;
 }
 
+// ---- multi-pass integration (R6Buffers.work given): the integrator cut at RK-attempt boundaries -------------------
+// A warp pays for the slowest of its 32 envs, and the attempt count of a step is 1 for a third of the envs, 2 for
+// most and 3-4 for ~1 %: in one kernel a warp runs 2.26 attempts for a mean of 1.64.  Here every pass runs ONE
+// attempt per env (the first one also the initial-step probe) and compacts the unfinished envs into a work list for
+// the next pass, so lanes never idle through an attempt they do not need:
+//   integrate_first_kernel   all envs of the range: probe + attempt 1            -> list 0
+//   integrate_resume_kernel  list 0: attempt 2                                   -> list 1
+//   integrate_resume_kernel  list 1: the remaining attempts (budget unlimited)
+// Carried per unfinished env: (t, h_abs, reference height of the density series) + (attempts, rejected) — see
+// integrate<..., kPass>; y is already in `state`.  The per-env arithmetic is that of integrate_kernel bit for bit.
+constexpr int kMaxLanes = R6_MAX_LANES;
+struct WorkView {
+    int32_t *count;          // [2 * kMaxLanes] entries of list l of lane a: count[2 a + l]
+    int32_t *list[2];        // [n] env index; a range [i0, i1) uses the slots [i0, i1) of each array
+    int32_t *meta[2];        // [n] attempts | rejected << 8
+    double *ctx[2];          // [3][n] t, h_abs, h_ref
+};
+__host__ __device__ inline WorkView work_view(uint8_t *w, int64_t n)
+{
+    WorkView v;
+    v.count = reinterpret_cast<int32_t *>(w);
+    int32_t *q = reinterpret_cast<int32_t *>(w + 256);
+    v.list[0] = q; v.list[1] = q + n; v.meta[0] = q + 2 * n; v.meta[1] = q + 3 * n;
+    double *d = reinterpret_cast<double *>(w + 256 + 16 * n);
+    v.ctx[0] = d; v.ctx[1] = d + 3 * n;
+    return v;
+}
+
+template <class R>
+__device__ __forceinline__ void work_append(const WorkView &W, int64_t n, int dst, int lane, int64_t i0, bool unfinished,
+                                            int64_t i, const PassCtx<R> &px)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, unfinished);
+    if (m == 0) return;
+    const int lid = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lid == leader) base = atomicAdd(&W.count[2 * lane + dst], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (unfinished) {
+        const int64_t slot = i0 + base + __popc(m & ((1u << lid) - 1u));
+        W.list[dst][slot] = (int32_t)i;
+        W.meta[dst][slot] = px.natt | (px.rejected ? 256 : 0);
+        double *c = W.ctx[dst];
+        c[slot] = (double)px.t; c[n + slot] = (double)px.h_abs; c[2 * n + slot] = (double)px.h_ref;
+    }
+}
+
+template <class R, bool kExact>
+__global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
+integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
+                       uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
+{
+    const int64_t i = i0 + (int64_t)blockIdx.x * kIntThreads + threadIdx.x;
+    extern __shared__ double r6_smem[];
+    KShared<R, kIntThreads> K;
+    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    PassCtx<R> px;
+    bool unfinished = false;
+    if (i < i1) {
+        R *state = reinterpret_cast<R *>(b.state);
+        R y[14];
+#pragma unroll
+        for (int c = 0; c < 14; c++) y[c] = state[(int64_t)c * n + i];
+        float a0, a1, a2;
+        if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
+        else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
+        int natt;
+        px.budget = 1;
+        const int status = env_integrate_pass<kExact, 1>(p, b.t_table, y, b.m0[i], b.step_count[i], a0, a1, a2, K, px, natt);
+#pragma unroll
+        for (int c = 0; c < 14; c++) state[(int64_t)c * n + i] = y[c];
+        unfinished = status == -2;
+        if (!unfinished) {
+            b.scratch[i] = (uint8_t)(int8_t)status;
+            b.scratch[n + i] = (uint8_t)natt;
+        }
+    }
+    work_append<R>(work_view(b.work, n), n, 0, lane, i0, unfinished, i, px);
+}
+
+template <class R, bool kExact>
+__global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
+integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
+                        uint64_t seed, int64_t step_index, int64_t i0, int lane, int src, int budget)
+{
+    extern __shared__ double r6_smem[];
+    KShared<R, kIntThreads> K;
+    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    const WorkView W = work_view(b.work, n);
+    const int64_t cnt = W.count[2 * lane + src];
+    R *state = reinterpret_cast<R *>(b.state);
+    for (int64_t s0 = (int64_t)blockIdx.x * kIntThreads; s0 < cnt; s0 += (int64_t)gridDim.x * kIntThreads) {
+        const int64_t slot = s0 + threadIdx.x;
+        PassCtx<R> px;
+        bool unfinished = false;
+        int64_t i = 0;
+        if (slot < cnt) {
+            i = W.list[src][i0 + slot];
+            const int meta = W.meta[src][i0 + slot];
+            const double *c = W.ctx[src];
+            px.t = (R)c[i0 + slot]; px.h_abs = (R)c[n + i0 + slot]; px.h_ref = (R)c[2 * n + i0 + slot];
+            px.natt = meta & 255; px.rejected = (meta & 256) != 0; px.budget = budget;
+            R y[14];
+#pragma unroll
+            for (int cc = 0; cc < 14; cc++) y[cc] = state[(int64_t)cc * n + i];
+            float a0, a1, a2;
+            if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
+            else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
+            int natt;
+            const int status = env_integrate_pass<kExact, 2>(p, b.t_table, y, b.m0[i], b.step_count[i], a0, a1, a2, K, px, natt);
+#pragma unroll
+            for (int cc = 0; cc < 14; cc++) state[(int64_t)cc * n + i] = y[cc];
+            unfinished = status == -2;
+            if (!unfinished) {
+                b.scratch[i] = (uint8_t)(int8_t)status;
+                b.scratch[n + i] = (uint8_t)natt;
+            }
+        }
+        if (src == 0) work_append<R>(W, n, 1, lane, i0, unfinished, i, px);
+    }
+}
+
 #ifndef R6_POST_BLOCKS
 #define R6_POST_BLOCKS 6         /* resident post-step CTAs per SM (no stage storage: registers are the only limit) */
 #endif
 template <class R>
 __global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
 post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
-            const float *__restrict__ actions, uint64_t seed, int64_t step_index, int64_t i0, int64_t i1)
+            const float *__restrict__ actions, uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
 {
     const int64_t i = i0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b.work != nullptr && blockIdx.x == 0 && threadIdx.x < 2)          // the lane's work lists are consumed: empty them
+        reinterpret_cast<int32_t *>(b.work)[2 * lane + threadIdx.x] = 0;
     if (i < i1) {
         EnvT<R> e;
         env_load(b, n, i, e);
@@ -697,6 +821,10 @@ int enable_all()
     rc |= enable_smem(step_kernel<R, true>, smem_bytes<R>());
     rc |= enable_smem(integrate_kernel<R, false>, smem_bytes<R>() * kIntThreads / kThreads);
     rc |= enable_smem(integrate_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_first_kernel<R, false>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_first_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, false>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, false>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, true>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, false>, smem_bytes<R>());
@@ -747,18 +875,31 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
 template <class R>
 void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset,
                  const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0, int64_t first = 0,
-                 int64_t count = -1)
+                 int64_t count = -1, int lane = 0)
 {
     if (b->scratch != nullptr) {                 // kernel pair over the env sub-range [first, first + count)
         if (count < 0) count = n;
+        const int64_t last = first + count;
         const unsigned gi = (unsigned)((count + kIntThreads - 1) / kIntThreads);
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
-        if (p->dt <= kMaxDtSeries)
-            integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, first + count);
+        const bool series = p->dt <= kMaxDtSeries;
+        if (b->work != nullptr) {                // integrator cut at attempt boundaries (see integrate_first_kernel)
+            // list 0 holds ~2/3 of the range, list 1 ~1 %; the resume kernels walk longer lists with a grid stride
+            const unsigned g1 = gi - gi / 4, g2 = gi / 16 + 1;
+            if (series) {
+                integrate_first_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
+                integrate_resume_kernel<R, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 0, 1);
+                integrate_resume_kernel<R, false><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 1, 1 << 30);
+            } else {
+                integrate_first_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
+                integrate_resume_kernel<R, true><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 0, 1);
+                integrate_resume_kernel<R, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 1, 1 << 30);
+            }
+        } else if (series)
+            integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
         else
-            integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, first + count);
-        post_kernel<R><<<(unsigned)blocks_for(count), kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first,
-                                                                      first + count);
+            integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
+        post_kernel<R><<<(unsigned)blocks_for(count), kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
         return;
     }
     const unsigned g = (unsigned)blocks_for(n);
@@ -847,20 +988,23 @@ int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env
     return check_launch("r6_step_random");
 }
 
-int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count, int64_t env_offset,
-                  const float *actions, uint64_t seed, int64_t step_index, void *stream)
+int64_t r6_work_bytes(int64_t n) { return n < 0 ? 0 : 256 + 64 * n; }
+
+int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count, int32_t lane,
+                  int64_t env_offset, const float *actions, uint64_t seed, int64_t step_index, void *stream)
 {
     int rc = validate_step(p, b, n);
     if (rc) return rc;
     if (!b->scratch) return fail(R6_EINVAL, "r6_step_range needs R6Buffers.scratch%s");
     if (first < 0 || count < 0 || first + count > n) return fail(R6_EINVAL, "env sub-range outside [0, n)%s");
+    if (lane < 0 || lane >= R6_MAX_LANES) return fail(R6_EINVAL, "lane outside [0, R6_MAX_LANES)%s");
     if (count == 0) return R6_OK;
     if ((rc = ensure_attributes())) return rc;
     const Derived dv = make_derived(*p);
     if (p->precision == R6_PREC_F32)
-        launch_step<float>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count);
+        launch_step<float>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count, lane);
     else
-        launch_step<double>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count);
+        launch_step<double>(p, b, dv, n, env_offset, actions, seed, (cudaStream_t)stream, step_index, first, count, lane);
     return check_launch("r6_step_range");
 }
 
