@@ -419,19 +419,22 @@ def run_b200(args):
                    "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"index-range shards x{world}",
                    "l2": "per-step working set 336 B x envs = %.0f MB > 126 MB L2" % (n * 336 / 1e6),
                    "preroll_steps": args.preroll, "mean_rk_attempts": mean_att,
-                   "stream_lanes": env.lanes,
+                   "stream_lanes": env.lanes, "multipass_integrator": env.work is not None,
                    "streams": (f"each step runs as {env.lanes} contiguous env sub-ranges on {env.lanes} CUDA streams "
                                "(r6_step_range), forked from and joined back into the timed stream around the K steps"
                                if env.lanes > 1 else "one stream")},
-        "gpu_launches": K * (2 if env.scratch is not None else 1) * env.lanes,
+        "gpu_launches": K * (4 if env.work is not None else 2 if env.scratch is not None else 1) * env.lanes,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
                      "frac": ach_tf / peaks["fp64"], "traffic": traffic, "traffic_unit": "B/launch",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": BYTES_PER_STEP * n,
                      "note": "algorithmic flops/env-step = 985 + 1850 x RK attempts (SURVEY 8d) x envs per launch; "
                              "peak = DFMA micro-benchmark measured in this run (r6_peak_fma)",
                      "flops_per_env_step": flops_step,
-                     "kernel": (f"integrate_kernel + post_kernel (r6_step as two launches per lane, {env.lanes} lane(s)); "
-                                "launch_ms = the whole env-step") if env.scratch is not None else "step_kernel",
+                     "kernel": ((f"integrate_first_kernel + 2 x integrate_resume_kernel + post_kernel (r6_step with the multi-pass "
+                                 f"integrator: four launches per lane, {env.lanes} lane(s)); launch_ms = the whole env-step")
+                                if env.work is not None else
+                                (f"integrate_kernel + post_kernel (r6_step as two launches per lane, {env.lanes} lane(s)); "
+                                 "launch_ms = the whole env-step") if env.scratch is not None else "step_kernel"),
                      "launch_ms": ms_step},
         "step_joined_every_step": {"value": world * n * K / (ms_joined * 1e-3), "unit": UNIT, "ms_per_step": ms_joined / K,
                                    "what": "same K steps with the lanes joined into the caller's stream after every step "

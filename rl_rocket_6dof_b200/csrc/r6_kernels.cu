@@ -65,6 +65,10 @@ constexpr int kIntThreads = R6_INT_THREADS;
 #define R6_INT_CTAS_F32 (R6_MIN_BLOCKS_F32 * R6_THREADS / R6_INT_THREADS)
 #endif
 template <class R> constexpr int int_ctas() { return sizeof(R) == 4 ? R6_INT_CTAS_F32 : R6_INT_CTAS_F64; }
+#ifndef R6_FIRST_CTAS_F64
+#define R6_FIRST_CTAS_F64 R6_INT_CTAS_F64       /* resident CTAs per SM of the first pass of the multi-pass integrator */
+#endif
+template <class R> constexpr int first_ctas() { return sizeof(R) == 4 ? R6_INT_CTAS_F32 : R6_FIRST_CTAS_F64; }
 // stage storage per CTA: 55,296 B (float64) / 27,648 B (float32); + packed policy weights (42,000 B) for R6_ACT_MLP
 template <class R> constexpr int smem_bytes() { return 6 * r6::kNK * kThreads * (int)sizeof(R); }
 template <class R> constexpr int smem_mlp_bytes() { return smem_bytes<R>() + r6::kMlpFloats * (int)sizeof(float); }
@@ -324,7 +328,7 @@ __device__ __forceinline__ void work_append(const WorkView &W, int64_t n, int ds
 }
 
 template <class R, bool kExact>
-__global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
+__global__ void __launch_bounds__(kIntThreads, first_ctas<R>())
 integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
                        uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
 {
