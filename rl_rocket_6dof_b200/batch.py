@@ -23,6 +23,7 @@ F_EVENT, F_OOB, F_TRUNCATED = 0x01, 0x02, 0x04
 F_LANDING_ALL = 0xF8
 FLAG_NAMES = ["zero_height", "velocity_limit", "landing_radius", "attitude_limit", "omega_limit"]
 SPLIT_MIN_ENVS = 65536
+MULTIPASS_MIN_ENVS = 1 << 19   # smallest batch the multi-pass integrator is the default for (float64 kernel pair)
 STAT_NAMES = ["episodes", "return_sum", "length_sum", "landed", "ground", "out_of_bounds", "truncated", "steps"]
 
 
@@ -99,11 +100,13 @@ class Rocket6DOFBatch:
             self._lanes_pending = False
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
             # multi-pass integrator (R6Buffers.work): one RK attempt per pass, unfinished envs compacted into work
-            # lists for the next pass; on with the float64 kernel pair unless asked otherwise (+4.4 % there; the
-            # float32 integrator is issue-bound and loses 1.5 % to the extra passes)
+            # lists for the next pass; on with the float64 kernel pair for large batches unless asked otherwise (+4 %
+            # at 2^20 envs, +6 % beyond; below 2^19 the four small launches cost more than the idle lanes did; the
+            # float32 integrator is issue-bound and loses 1.5 % to the extra passes) — profiles/r01_sweep_envs_v11*
             if multipass is None:
                 env_flag = os.environ.get("R6_MULTIPASS")
-                multipass = (split_step and precision == "fp64") if env_flag is None else (env_flag != "0" and split_step)
+                multipass = ((split_step and precision == "fp64" and n >= MULTIPASS_MIN_ENVS) if env_flag is None
+                             else (env_flag != "0" and split_step))
             if multipass and not split_step:
                 raise ValueError("multipass needs the split step (split_step=True)")
             self.work = torch.zeros(int(self.lib.r6_work_bytes(n)), dtype=torch.uint8, device=dev) if multipass else None

@@ -103,15 +103,17 @@ def test_policy_closed_loop_action_replay():
     replay_record(env_params(), golden("policy_cl"), flips=40)
 
 
-def test_split_step_kernels_vs_oracle():
-    """r6_step as the integrator | post-step kernel pair (forced for a small batch; large batches use it by default)
+@pytest.mark.parametrize("multipass,lanes", [(False, 1), (True, 1), (True, 2)])
+def test_split_step_kernels_vs_oracle(multipass, lanes):
+    """r6_step as the integrator | post-step kernel pair (forced for a small batch; large batches use it by default),
+    with the integrator as one kernel or cut into passes at RK-attempt boundaries, on one stream or two lanes,
     against the C oracle: 4096 envs x 60 random-action steps, same bars as the fused kernel."""
     import torch
     from oracle import c_oracle as co
     ep = env_params()
     n, K = 4096, 60
-    env = make_batch(n, ep, split_step=True, seed=77)
-    assert env.scratch is not None
+    env = make_batch(n, ep, split_step=True, multipass=multipass, lanes=lanes, seed=77)
+    assert env.scratch is not None and (env.work is not None) == multipass
     env.reset()
     torch.cuda.synchronize()
     ic = env.state.t().cpu().numpy()
