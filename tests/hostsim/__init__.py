@@ -42,6 +42,8 @@ def lib():
         L.hs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
         L.hs_sim_step_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
+        L.hs_sim_step_raw_passes.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int)]
         L.hs_euler_tests.argtypes = [C.c_void_p] * 3 + [C.POINTER(C.c_int)] * 2
         L.hs_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
         L.hs_philox_action.argtypes = [C.c_uint64] * 3 + [C.c_void_p]

@@ -76,6 +76,36 @@ int hs_sim_step_raw(double *y, const double *u, double m0, double t, double dt, 
     return st;
 }
 
+// The same solve_ivp call cut at RK-attempt boundaries the way integrate_first_kernel / integrate_resume_kernel do:
+// one attempt per pass, and between passes NOTHING survives but y and the PassCtx (fresh constants, fresh stage
+// storage), which is exactly what the work lists carry on the device.
+int hs_sim_step_raw_passes(double *y, const double *u, double m0, double t, double dt, int *natt, int *passes)
+{
+    PassCtx<double> px;
+    px.budget = 1;
+    int st;
+    {
+        StepConst c;
+        consts_raw_mode(c, m0, u[0], u[1], u[2], y[10]);
+        KLocal K;
+        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 1>(c, y, t, dt, *natt, K, &px)
+                                  : integrate<true, KLocal, double, 1>(c, y, t, dt, *natt, K, &px);
+    }
+    *passes = 1;
+    while (st == -2) {
+        StepConst c;
+        consts_raw_mode(c, m0, u[0], u[1], u[2], y[10]);
+        KLocal K;
+        memset(&K, 0, sizeof K);
+        px.budget = 1;
+        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 2>(c, y, t, dt, *natt, K, &px)
+                                  : integrate<true, KLocal, double, 2>(c, y, t, dt, *natt, K, &px);
+        (*passes)++;
+    }
+    normalize_quat(y);
+    return st;
+}
+
 double hs_tgo(double c0, double c2, double c3, double c4) { return tgo_largest_root(c0, c2, c3, c4); }
 
 void hs_euler_tests(const double viol[3], const double land[3], const double q[4], int *violated, int *land_ok)

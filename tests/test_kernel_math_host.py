@@ -99,6 +99,47 @@ def test_host_raw_simulator():
         assert np.max(np.abs(y - g["run_state"][k]) / np.maximum(np.abs(g["run_state"][k]), 1e-3)) <= 1e-10
 
 
+def test_host_integrator_cut_into_passes_is_bit_identical():
+    """integrate<kPass = 1 / 2> (one RK attempt per pass, only y + PassCtx carried, as the multi-pass kernels do) ==
+    the single-call integrator bit for bit, on the config1 trajectory (1000 recorded states / controls, including the
+    touchdown steps with the event path and the rare 3-attempt steps)."""
+    g = golden("config1")
+    L = hostsim.lib()
+    m0 = {int(s): float(ic[13]) for s, ic in zip(g["ic_step"], g["ic"]) if s >= 0}
+    cur_m0, npass = None, {}
+    n3 = 0
+    for k in range(len(g["action"]) - 1):
+        if k in m0:
+            cur_m0 = m0[k]
+        if g["done"][k]:
+            continue                                   # state[k] is terminal: the next record starts from a new IC
+        y0 = np.ascontiguousarray(g["state"][k], np.float64)
+        u = np.ascontiguousarray(g["u"][k + 1], np.float64)
+        t = round(0.1 * (k % 50), 3)
+        ya, yb = y0.copy(), y0.copy()
+        na, nb, ps = C.c_int(0), C.c_int(0), C.c_int(0)
+        sa = L.hs_sim_step_raw(ya.ctypes.data, u.ctypes.data, cur_m0, t, 0.1, C.byref(na))
+        sb = L.hs_sim_step_raw_passes(yb.ctypes.data, u.ctypes.data, cur_m0, t, 0.1, C.byref(nb), C.byref(ps))
+        assert sa == sb and na.value == nb.value and ps.value == nb.value, k
+        assert np.array_equal(ya, yb), k
+        npass[ps.value] = npass.get(ps.value, 0) + 1
+        n3 += nb.value >= 3
+    assert npass.get(1, 0) > 50 and npass.get(2, 0) > 50, npass
+    # a longer step makes every call multi-pass, with rejected attempts and ground contact among them
+    rng = np.random.default_rng(0)
+    many = 0
+    for k in rng.choice(len(g["action"]) - 1, 200, replace=False):
+        y0 = np.ascontiguousarray(g["state"][k], np.float64)
+        u = np.ascontiguousarray(g["u"][k], np.float64)
+        ya, yb = y0.copy(), y0.copy()
+        na, nb, ps = C.c_int(0), C.c_int(0), C.c_int(0)
+        sa = L.hs_sim_step_raw(ya.ctypes.data, u.ctypes.data, 41000.0, 0.0, 2.0, C.byref(na))
+        sb = L.hs_sim_step_raw_passes(yb.ctypes.data, u.ctypes.data, 41000.0, 0.0, 2.0, C.byref(nb), C.byref(ps))
+        assert sa == sb and na.value == nb.value == ps.value and np.array_equal(ya, yb), k
+        many += nb.value >= 3
+    assert many > 20
+
+
 def test_host_tgo_vs_np_roots():
     u = golden("units")
     L = hostsim.lib()
