@@ -90,8 +90,8 @@ class Rocket6DOFBatch:
             # 0.454 ms when every step is joined back into the caller's stream (profiles/two_stream_shards.py)
             self.lanes = max(int(lanes), 1)
             if self.lanes > 1:
-                if n < self.lanes:
-                    raise ValueError("more lanes than envs")
+                if n < self.lanes or self.lanes > 32:          # R6_MAX_LANES
+                    raise ValueError("lanes must be <= min(num_envs, 32)")
                 split_step = True
                 self._lane_streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
                 base, rem = divmod(n, self.lanes)
