@@ -58,6 +58,7 @@ class Rocket6DOFVecEnv:
         self._done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
         self._flags_h = torch.empty(n, dtype=torch.uint8).pin_memory()
         self._actions = None
+        self._act_in_flight = None
         self._empty_infos: List[dict] = [{} for _ in range(n)]
         self._t_start = time.time()
         self.zero_copy = bool(zero_copy)
@@ -95,6 +96,11 @@ class Rocket6DOFVecEnv:
         (pinned) actions and writes obs / reward / done / flags straight to host memory over PCIe — the device-side
         `batch.obs` is then NOT refreshed (use `batch.step` / `batch.policy_*` for device-resident loops).
         zero_copy=False: host->device copy, step kernels, device->host copies."""
+        self._launch_host_step(actions)
+        return self._finish_host_step()
+
+    def _launch_host_step(self, actions) -> None:
+        """Everything of `step_host` up to (not including) the wait for the device: returns once the work is enqueued."""
         b = self.batch
         a = torch.as_tensor(actions, dtype=torch.float32).reshape(self.num_envs, 3)
         if self.zero_copy:
@@ -102,13 +108,14 @@ class Rocket6DOFVecEnv:
             if not (a.is_pinned() and a.is_contiguous()):
                 self._act_h.copy_(a)
                 a = self._act_h
+            self._act_in_flight = a                 # keep the pinned source alive until the kernel has read it
             with torch.cuda.device(b.device):
                 _lib.check(b.lib.r6_step(C.byref(self._p_host), C.byref(self._b_host), self.num_envs, b.env_offset,
                                          a.data_ptr(), b.seed_value, b._stream()), b.lib)
             b.steps_done += 1
-            torch.cuda.current_stream(b.device).synchronize()
-            return self._obs_rm.numpy(), self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
+            return
         if a.is_pinned():                      # caller already staged the actions in pinned memory
+            self._act_in_flight = a
             self._act_d.copy_(a, non_blocking=True)
         else:
             self._act_h.copy_(a)
@@ -118,7 +125,13 @@ class Rocket6DOFVecEnv:
         self._rew_h.copy_(b.reward_f32, non_blocking=True)
         self._done_h.copy_(b.done, non_blocking=True)
         self._flags_h.copy_(b.flags, non_blocking=True)
+
+    def _finish_host_step(self) -> tuple:
+        b = self.batch
         torch.cuda.current_stream(b.device).synchronize()
+        self._act_in_flight = None
+        if self.zero_copy:
+            return self._obs_rm.numpy(), self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
         return self._obs_h.numpy().T, self._rew_h.numpy(), self._done_h.numpy().view(np.bool_)
 
     # ------------------------------------------------------------------ SB3 VecEnv protocol
@@ -126,10 +139,15 @@ class Rocket6DOFVecEnv:
         return np.ascontiguousarray(self.reset_host())
 
     def step_async(self, actions) -> None:
-        self._actions = np.asarray(actions, dtype=np.float32)
+        """Enqueues the step and returns (the SubprocVecEnv contract: the caller may work until `step_wait`)."""
+        self._launch_host_step(np.asarray(actions, dtype=np.float32))
+        self._actions = True
 
     def step_wait(self):
-        obs, rews, dones = self.step_host(self._actions)
+        if self._actions is None:
+            raise RuntimeError("step_wait without step_async")
+        self._actions = None
+        obs, rews, dones = self._finish_host_step()
         # [N, obs_dim] contiguous: torch's blocked transpose-copy of the pinned [obs_dim, N] buffer is several times
         # faster than numpy's strided copy
         obs = obs.copy() if obs.flags["C_CONTIGUOUS"] else self._obs_h.t().contiguous().numpy()

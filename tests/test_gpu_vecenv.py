@@ -105,3 +105,26 @@ def test_gym_facade_known_answer():
     assert abs(env.used_mass() - (rec["ic"][0][13] - rec["state"][2][13])) <= 1e-6
     with pytest.raises(KeyError):
         Rocket6DOF(IC=cfg["IC"], ICRange=cfg["ICRange"], device="cuda:0")     # no landing_params -> 'waypoint'
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_step_async_returns_before_the_step_is_done(zero_copy):
+    """step_async only enqueues (SubprocVecEnv contract); step_wait delivers what step() would have; the caller may
+    overwrite its action array in between."""
+    from rl_rocket_6dof_b200 import make_vec_env
+    n, k = 2048, 40
+    a = _actions(n, k, seed=5)
+    e1 = make_vec_env(n, seed=9, zero_copy=zero_copy)
+    e2 = make_vec_env(n, seed=9, zero_copy=zero_copy)
+    o1, o2 = e1.reset(), e2.reset()
+    assert np.array_equal(o1, o2)
+    with pytest.raises(RuntimeError):
+        e1.step_wait()
+    for j in range(k):
+        buf = a[j].copy()
+        e1.step_async(buf)
+        buf[:] = 7.0                                   # the env must not still be reading the caller's array
+        r1 = e1.step_wait()
+        r2 = e2.step(a[j])
+        assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+        assert [sorted(d) for d in r1[3]] == [sorted(d) for d in r2[3]]
