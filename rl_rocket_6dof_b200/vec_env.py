@@ -32,6 +32,17 @@ from .batch import F_EVENT, F_OOB, F_TRUNCATED, F_LANDING_ALL, FLAG_NAMES, Rocke
 from .spaces import make_box
 
 
+def _flag_info(f: int) -> dict:
+    """The info entries that depend only on the step's flag byte (R6_F_*)."""
+    return {"TimeLimit.truncated": bool(f & F_TRUNCATED), "is_done": bool(f & (F_EVENT | F_OOB)),
+            "bounds_violation": bool(f & F_OOB),
+            "landing_conditions": {nm: bool(f & (8 << k)) for k, nm in enumerate(FLAG_NAMES)},
+            "is_successful": (f & F_LANDING_ALL) == F_LANDING_ALL}
+
+
+_FLAG_INFO = [_flag_info(f) for f in range(256)]       # templates: copied per finished env, never handed out
+
+
 class MonitorTag:
     """Stands for stable_baselines3.common.monitor.Monitor in `env_is_wrapped` queries."""
 
@@ -161,20 +172,17 @@ class Rocket6DOFVecEnv:
             tobs = b.terminal_obs[: self.obs_dim][:, sel].t().cpu().numpy()
             tstate = b.terminal_state[:, sel].t().cpu().numpy()
             epi = b.ep_info[:, sel].cpu().numpy()
-            fl = self._flags_h.numpy()[idx]
+            fl = self._flags_h.numpy()[idx].tolist()
+            ret, length = epi[0].tolist(), epi[1].astype(np.int64).tolist()
             now = round(time.time() - self._t_start, 6)
-            for j, i in enumerate(idx):
-                f = int(fl[j])
-                infos[i] = {
-                    "terminal_observation": tobs[j],
-                    "episode": {"r": float(epi[0, j]), "l": int(epi[1, j]), "t": now},
-                    "TimeLimit.truncated": bool(f & F_TRUNCATED),
-                    "is_done": bool(f & (F_EVENT | F_OOB)),
-                    "bounds_violation": bool(f & F_OOB),
-                    "landing_conditions": {nm: bool(f & (8 << k)) for k, nm in enumerate(FLAG_NAMES)},
-                    "is_successful": (f & F_LANDING_ALL) == F_LANDING_ALL,
-                    "state_history": [tstate[j]],
-                }
+            for j, i in enumerate(idx.tolist()):
+                tpl = _FLAG_INFO[fl[j]]
+                d = dict(tpl)
+                d["landing_conditions"] = dict(tpl["landing_conditions"])
+                d["terminal_observation"] = tobs[j]
+                d["episode"] = {"r": ret[j], "l": length[j], "t": now}
+                d["state_history"] = [tstate[j]]
+                infos[i] = d
         return obs, rews.copy(), dones.copy(), infos
 
     def step(self, actions):
