@@ -5,15 +5,16 @@
 
 A "step" is one Rocket6DOF env-step for every env of the batch (workload: BASELINE.json configs[2],
 2^20 envs per GPU, uniform random actions, auto-reset on).  Rank 0 prints ONE JSON line:
-  value      whole-job env-steps/s, one r6_step call (two kernel launches: integrator | post-step) per env-step,
-             actions already in HBM
+  value      whole-job env-steps/s, one Rocket6DOFBatch.step call per env-step, actions already in HBM, the outputs
+             (obs / reward / done) ordered on the caller's stream after EVERY step (what a per-step consumer gets);
+             `free_running` = the same K steps with the stream lanes joined only once at the end
   e2e        the same through Rocket6DOFVecEnv.step_host: pinned-host actions in, H2D copy, kernel,
              D2H copy of obs/reward/done/flags every step
   roofline   the step kernel against the measured FP64 FMA-pipe peak (bound "fp64"; the dynamics are
              not a contraction and sit above the HBM ridge) and roofline_hbm against MEASURED_PEAKS
   cpu_baseline  the CPU oracle (C restatement, all host threads) on a bounded sample of the workload
---impl reference times the CPU restatements of the reference (Python/SciPy port under a
-SubprocVecEnv-like harness; the C oracle's number is reported beside it).
+--impl reference times the UNMODIFIED reference env (baseline/_ref) under a SubprocVecEnv-protocol harness on the
+host cores (the Python/SciPy port's and the C oracle's numbers are reported beside it).
 """
 import argparse
 import json
@@ -45,6 +46,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=32768)
     ap.add_argument("--cpu-sample-steps", type=int, default=100)
+    ap.add_argument("--ref-steps-per-worker", type=int, default=1000,
+                    help="--impl reference: env-steps per worker process over the whole timed run (BASELINE.md §3)")
+    ap.add_argument("--cpu-ref-steps", type=int, default=400,
+                    help="cpu_baseline leg of the default run: VecEnv.step calls of the reference env per worker")
+    ap.add_argument("--config4-envs", type=int, default=1 << 23,
+                    help="envs per GPU of the BASELINE.json configs[3] leg (runs when WORLD_SIZE == 8; 0 = off)")
     return ap.parse_args()
 
 
@@ -149,38 +156,63 @@ def cpu_oracle_throughput(n_envs, n_steps, threads):
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_throughput(vec_steps, warmup):
+    """The reference's own CPU implementation of the path: the UNMODIFIED env from baseline/_ref under the
+    SubprocVecEnv-protocol harness, one worker per host core (baseline/ref_arm.py).  Returns
+    (result dict, kind); falls back to the Python/SciPy port (kind "port") only when baseline/_ref did not travel."""
+    cores = os.cpu_count() or 1
+    from baseline import ref_arm
+    if ref_arm.available():
+        return ref_arm.time_reference(cores, vec_steps, warmup), "reference"
+    from oracle import subproc_vec_env as sv
+    return sv.time_python_port(n_workers=cores, steps=vec_steps, warmup=warmup), "port"
+
+
 def run_reference(args):
-    """CPU arm: the reference's algorithm on the host cores, all threads.  /root/reference is pure
-    Python and cannot travel to the GPU box, so the timed code is its restatement under oracle/."""
+    """CPU arm (rank 0 only): `--steps K` bench steps, each a block of ceil(1000 / K) VecEnv.step calls over one
+    single-env worker process per host core (so the run covers >= 1000 env-steps per worker), after
+    max(50, W) untimed VecEnv.step calls."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    K = max(args.steps, 1)
+    block = max(1, -(-args.ref_steps_per_worker // K))
+    warm = max(50, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0}
-    py = None
-    try:
-        from oracle import subproc_vec_env as sv
-        # each bench step = one VecEnv.step over `cores` workers x envs_per_worker python envs
-        py = sv.time_python_port(n_workers=cores, steps=max(args.steps, 1) * 4, warmup=max(args.warmup, 1) * 4)
-    except Exception as e:  # pragma: no cover
-        line["python_port_error"] = repr(e)[:200]
-    c_val = cpu_oracle_throughput(args.cpu_sample_envs, args.cpu_sample_steps, cores)
-    if py is not None:
-        value, kind_note = py["steps_per_s"], py["sample"]
-        ms = 1e3 * py["seconds"] / max(py["vec_steps"], 1)
-    else:
-        value, kind_note = c_val, f"C oracle, {args.cpu_sample_envs} envs x {args.cpu_sample_steps} steps"
-        ms = None
-    line.update(value=value, ms_per_step=ms,
-                config={"workload": "Rocket6DOF config.yaml, uniform random actions, auto-reset, make_env() wrappers; "
-                                    "CPU SubprocVecEnv-style harness, one worker per host core"},
-                cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": kind_note},
-                cpu_baseline_c_oracle={"value": c_val, "unit": UNIT, "cores": cores, "kind": "port",
-                                       "sample": f"oracle/r6_oracle.c, {args.cpu_sample_envs} envs x "
-                                                 f"{args.cpu_sample_steps} steps, pthreads"},
+    res, kind = reference_throughput(K * block, warm)
+    value = res["steps_per_s"]
+    marks = res.get("marks")
+    per_block = None
+    if marks:
+        import numpy as np
+        t = np.asarray(marks)
+        per_block = (cores * block / np.diff(t[::block])).tolist()          # env-steps/s of each bench step
+    line.update(value=value, ms_per_step=1e3 * res["seconds"] / K,
+                config={"workload": "Rocket6DOF config.yaml, uniform random actions, auto-reset, make_env() wrappers "
+                                    "(main_6DOF.py:44-53); CPU SubprocVecEnv-protocol harness, one single-env worker "
+                                    "process per host core; one bench step = %d VecEnv.step calls" % block,
+                           "vec_steps_per_bench_step": block, "workers": cores, "warmup_vec_steps": warm,
+                           "episodes_finished": res.get("episodes")},
+                cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": res["sample"]},
                 e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    if per_block:
+        line["per_step_values"] = {"min": min(per_block), "max": max(per_block), "median": statistics.median(per_block)}
+    if not args.no_cpu_baseline:
+        # beside it (not the arm's value): the restatements the parity tests use, on the same host cores
+        try:
+            from oracle import subproc_vec_env as sv
+            py = sv.time_python_port(n_workers=cores, steps=200, warmup=20)
+            line["cpu_baseline_python_port"] = {"value": py["steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                                                "sample": py["sample"]}
+        except Exception as e:  # pragma: no cover
+            line["python_port_error"] = repr(e)[:200]
+        c_val = cpu_oracle_throughput(args.cpu_sample_envs, args.cpu_sample_steps, cores)
+        line["cpu_baseline_c_oracle"] = {"value": c_val, "unit": UNIT, "cores": cores, "kind": "port",
+                                         "sample": f"oracle/r6_oracle.c, {args.cpu_sample_envs} envs x "
+                                                   f"{args.cpu_sample_steps} steps, pthreads"}
     print(json.dumps(line), flush=True)
 
 
@@ -247,14 +279,18 @@ def run_b200(args):
     env.join()
     e1.record(stream)
     torch.cuda.synchronize()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_free = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    # headline: every step joined back into the caller's stream (outputs consumable per step)
+    for w in range(W):
+        env.step(acts[w % R])
     barrier()
     e0.record(stream)
     for k in range(K):
         env.step(acts[k % R])
     e1.record(stream)
     torch.cuda.synchronize()
-    ms_joined = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     barrier()
     ms_step = ms_total / K
     value = world * n * K / (ms_total * 1e-3)
@@ -382,6 +418,37 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     e2e_value = world * n * K / (ms_e2e * 1e-3)
+    h2d_bytes, d2h_bytes = vec.h2d_bytes_per_step, vec.d2h_bytes_per_step
+
+    # ---- BASELINE.json configs[3]: 64 M envs sharded over 8 B200s (2^23 per GPU), NCCL episode-stat reduction ----
+    config4 = None
+    n4 = args.config4_envs
+    if world == 8 and n4 > 0:
+        del vec
+        torch.cuda.empty_cache()
+        env4 = Rocket6DOFBatch(n4, device=dev, seed=42, env_offset=rank * n4, num_envs_global=world * n4,
+                               record_attempts=True, lanes=args.lanes)
+        env4.reset()
+        env4.rollout(args.preroll)
+        acts4 = (torch.rand(2, n4, 3, device=dev, generator=gen) * 2 - 1).contiguous()
+        for w in range(W):
+            env4.step(acts4[w % 2])
+        env4.reset_stats()
+        barrier()
+        K4 = max(K // 2, 4)
+        e0.record(stream)
+        for k in range(K4):
+            env4.step(acts4[k % 2])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms4 = max_over_ranks(e0.elapsed_time(e1))
+        att4 = float(env4.nattempts.to(torch.float64).mean())
+        stats4 = env4.stats.clone()
+        dist.all_reduce(stats4)                    # the NCCL episode-statistics reduction of config 4
+        sd4 = env4.stats_dict(stats4)
+        config4 = {"ms": ms4, "steps": K4, "mean_att": att4, "stats": sd4}
+        barrier()
+        del env4, acts4
 
     # ---- FP64 / FP32 FMA-pipe peak, measured here (MEASURED_PEAKS.json has none) -------------
     sink = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -420,8 +487,9 @@ def run_b200(args):
                    "l2": "per-step working set 336 B x envs = %.0f MB > 126 MB L2" % (n * 336 / 1e6),
                    "preroll_steps": args.preroll, "mean_rk_attempts": mean_att,
                    "stream_lanes": env.lanes, "multipass_integrator": env.work is not None,
+                   "value_is": "joined every step: obs/reward/done are ordered on the caller's stream after each step",
                    "streams": (f"each step runs as {env.lanes} contiguous env sub-ranges on {env.lanes} CUDA streams "
-                               "(r6_step_range), forked from and joined back into the timed stream around the K steps"
+                               "(r6_step_range), forked from and joined back into the timed stream around EVERY step"
                                if env.lanes > 1 else "one stream")},
         "gpu_launches": K * (4 if env.work is not None else 2 if env.scratch is not None else 1) * env.lanes,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peaks["fp64"], "unit": "TFLOP/s",
@@ -436,9 +504,9 @@ def run_b200(args):
                                 (f"integrate_kernel + post_kernel (r6_step as two launches per lane, {env.lanes} lane(s)); "
                                  "launch_ms = the whole env-step") if env.scratch is not None else "step_kernel"),
                      "launch_ms": ms_step},
-        "step_joined_every_step": {"value": world * n * K / (ms_joined * 1e-3), "unit": UNIT, "ms_per_step": ms_joined / K,
-                                   "what": "same K steps with the lanes joined into the caller's stream after every step "
-                                           "(outputs consumable on that stream per step)"},
+        "free_running": {"value": world * n * K / (ms_free * 1e-3), "unit": UNIT, "ms_per_step": ms_free / K,
+                         "what": "same K steps with the stream lanes left running and joined into the caller's stream "
+                                 "once after the last step (outputs NOT ordered per step; not the headline)"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gb / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_STEP},
@@ -474,19 +542,29 @@ def run_b200(args):
         "ppo_collect_rollout": {"value": world * n * KC / (ms_collect * 1e-3), "unit": UNIT, "ms_per_step": ms_collect / KC,
                                 "steps": KC, "what": "stochastic Gaussian policy + value head (r6_policy_ex, tcgen05 mode), r6_step, "
                                                      "[T,N] buffers written on the device, then the GAE scan (r6_gae)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": vec.h2d_bytes_per_step,
-                "d2h_bytes_per_step": vec.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K,
                 "api": "Rocket6DOFVecEnv.step_host (pinned host actions -> obs/reward/done on the host)"},
         "numa_node_rank0": numa_node,
+        "config4": None if config4 is None else {
+            "workload": f"configs[3]: {world} x {n4} = {world * n4} envs (2^{int(np.log2(world * n4))}), index-range shards, "
+                        "uniform random actions resident in HBM, joined every step, NCCL all_reduce of the episode statistics",
+            "value": world * n4 * config4["steps"] / (config4["ms"] * 1e-3), "unit": UNIT, "steps": config4["steps"],
+            "ms_per_step": config4["ms"] / config4["steps"], "mean_rk_attempts": config4["mean_att"],
+            "roofline_frac_fp64": n4 / (config4["ms"] / config4["steps"] * 1e-3) * (F_FIX + F_ATT * config4["mean_att"]) / 1e12 / peaks["fp64"],
+            "episode_stats": {k: config4["stats"][k] for k in ("episodes", "mean_return", "mean_length", "landing_rate", "steps")}},
         "episode_stats": {k: sd[k] for k in ("episodes", "mean_return", "mean_length", "landing_rate", "steps")},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
+        res, kind = reference_throughput(args.cpu_ref_steps, 50)
+        line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": res["sample"]}
         v = cpu_oracle_throughput(args.cpu_sample_envs, args.cpu_sample_steps, cores)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle/r6_oracle.c (C restatement), {args.cpu_sample_envs} envs x "
-                                          f"{args.cpu_sample_steps} steps of the same workload, pthreads"}
+        line["cpu_baseline_c_oracle"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                         "sample": f"oracle/r6_oracle.c (C restatement), {args.cpu_sample_envs} envs x "
+                                                   f"{args.cpu_sample_steps} steps of the same workload, pthreads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -63,3 +63,17 @@ class RewardWrapper(Wrapper):
     def step(self, action):
         o, r, d, i = self.env.step(action)
         return o, self.reward(r), d, i
+
+
+def make(id, **kwargs):
+    """gym.make for ids registered through gym.envs.registration.register (entry_point 'module:Class')."""
+    import importlib
+    from .envs.registration import REGISTRY
+    entry = REGISTRY[id]
+    if isinstance(entry, str):
+        mod, _, name = entry.partition(":")
+        entry = getattr(importlib.import_module(mod), name)
+    return entry(**kwargs)
+
+
+from . import wrappers  # noqa: E402,F401

@@ -3,7 +3,8 @@
 Stands in for stable_baselines3.common.vec_env.SubprocVecEnv (SB3 is not installed in this image):
 one worker process per env, `step` / `reset` / `close` commands over a Pipe, auto-reset on done with
 `terminal_observation`, exactly SB3's worker protocol.  Used only to time the CPU arm
-(oracle/py_port.py) for bench.py --impl reference and BASELINE.md's CPU-baseline plan.
+(the unmodified reference env from baseline/_ref, or oracle/py_port.py beside it) for bench.py --impl reference and
+BASELINE.md's CPU-baseline plan.
 """
 from __future__ import annotations
 
@@ -18,15 +19,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(remote, parent_remote, seed):
+def _make_port_env(seed):
+    from oracle.py_port import WrappedPort
+    from rl_rocket_6dof_b200.params import derive_params, load_config
+    sb3, cfg = load_config()
+    return WrappedPort(derive_params(cfg, sb3), seed)
+
+
+def _worker(remote, parent_remote, seed, env_fn):
     parent_remote.close()
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     warnings.filterwarnings("ignore")
-    from oracle.py_port import WrappedPort
-    from rl_rocket_6dof_b200.params import derive_params, load_config
-    sb3, cfg = load_config()
-    env = WrappedPort(derive_params(cfg, sb3), seed)
+    env = (env_fn or _make_port_env)(seed)
     try:
         while True:
             cmd, data = remote.recv()
@@ -46,13 +51,15 @@ def _worker(remote, parent_remote, seed):
 
 
 class SubprocVecEnvPort:
-    def __init__(self, n_envs, seed0=42):
+    def __init__(self, n_envs, seed0=42, env_fn=None):
+        """env_fn(seed) -> gym-style env, called inside each worker (default: the Python/SciPy port with the make_env()
+        wrappers; baseline/ref_arm.py passes the factory of the unmodified reference env)."""
         ctx = mp.get_context("fork")
         self.n = n_envs
         self.remotes, work = zip(*[ctx.Pipe() for _ in range(n_envs)])
         self.procs = []
         for i, (w, r) in enumerate(zip(work, self.remotes)):
-            p = ctx.Process(target=_worker, args=(w, r, seed0 + i), daemon=True)
+            p = ctx.Process(target=_worker, args=(w, r, seed0 + i, env_fn), daemon=True)
             p.start()
             self.procs.append(p)
             w.close()
