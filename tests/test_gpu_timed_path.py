@@ -33,17 +33,18 @@ def _fetch_idx(env, idx):
 
 
 @pytest.mark.parametrize("lanes", [1, 2])
-@pytest.mark.parametrize("dt", [0.5, 0.25])
+@pytest.mark.parametrize("dt", [1.0, 0.25])
 def test_multipass_long_work_lists_vs_oracle(dt, lanes):
-    """dt = 0.5 s / 0.25 s: every env needs a second RK attempt and 6-7 % a third or fourth, so the unfinished-env
-    lists of the multi-pass integrator are as long as the range itself (the resume launches are sized for the
-    random-action mix at dt = 0.1 s, where list 0 holds ~64 % and list 1 ~1 %) — each resume CTA walks more than one
-    tile.  8192 envs x 40 random-action steps against the C oracle."""
+    """dt = 0.25 s: every env needs a second RK attempt and ~6 % a third; dt = 1 s: half of them need three and 7 %
+    four to six — so the unfinished-env lists of the multi-pass integrator are as long as the range itself (the
+    resume launches are sized for the random-action mix at dt = 0.1 s, where list 0 holds ~64 % and list 1 ~1 %) and
+    each resume CTA walks more than one tile.  8192 envs x 40 (12 at dt = 1 s, where episodes are short) random-action
+    steps against the C oracle."""
     import torch
     from oracle import c_oracle as co
     from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
     ep = env_params(timestep=dt)
-    n, K = 8192, 40
+    n, K = 8192, (12 if dt == 1.0 else 40)
     env = Rocket6DOFBatch(n, params=ep, auto_reset=False, clip_reward=False, time_limit=False, debug_buffers=True,
                           split_step=True, multipass=True, lanes=lanes, seed=31)
     assert env.work is not None
@@ -72,9 +73,10 @@ def test_multipass_long_work_lists_vs_oracle(dt, lanes):
     frac = hist / hist.sum()
     print(f"dt={dt} lanes={lanes}: attempts histogram {np.round(frac[:6], 4)}, alive at the end {alive.sum()}")
     assert frac[2:].sum() > 0.75               # list 0 longer than 3/4 of the range
-    if dt == 0.5:
-        assert frac[3:].sum() > 0.0625         # list 1 longer than 1/16 of the range
-    assert alive.sum() > n // 4
+    if dt == 1.0:
+        assert frac[3:].sum() > 0.25           # list 1 far longer than 1/16 of the range
+        assert frac[4:].sum() > 0.02           # and a tail of 4-6 attempts
+    assert alive.sum() > (0 if dt == 1.0 else n // 8)
 
 
 def test_default_dispatch_1m_envs_sampled_vs_oracle():
