@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define R6_ABI_VERSION 15
+#define R6_ABI_VERSION 16
 #define R6_MAX_LANES 32
 #define R6_NSTATE 14
 #define R6_NTERMS 7
@@ -137,7 +137,8 @@ typedef struct R6Buffers {
     double *reward_terms;   /* [7][n] nullable: rewards_dict values in insertion order */
     uint8_t *nattempts;     /* [n] nullable: RK attempts of the step (nfev = 2 + 6*nattempts) */
     int8_t *status;         /* [n] nullable: solve_ivp status of the step (0, 1, -1) */
-    float *ep_info;         /* [2][n] nullable: (return, length) of the episode that just finished */
+    double *ep_info;        /* [2][n] nullable: (return, length) of the episode that just finished — float64 like the
+                               running sum Monitor reports (stable_baselines3 Monitor: info["episode"]["r"], ["l"]) */
     float *reward_f32;      /* [n] nullable: reward[] rounded to float32 (what a VecEnv hands to SB3) */
     /* tables */
     const double *t_table;  /* [n_t] t_k = round(t_{k-1}+dt, 3) (simulator.py:92) */
@@ -152,6 +153,10 @@ typedef struct R6Buffers {
                                When given, the integrator runs as three passes cut at RK-attempt boundaries, the
                                unfinished envs of a pass compacted into work lists for the next (a warp then never
                                idles through attempts only some of its envs need) */
+    float *tgo;             /* [n] nullable: t_go root of the env's previous step (0 = none; r6_reset and the auto-reset
+                               write 0), the warm start of the next step's root iteration (rocket_env.py:528-546).
+                               Results do not depend on it beyond round-off: a warm result is used only when certified
+                               to be the largest root, otherwise the cold start runs */
 } R6Buffers;
 
 /* Weights of the SB3 MlpPolicy actor (net_arch [128, 64], tanh), float32 row-major [out][in]. */
@@ -238,8 +243,9 @@ int r6_sim_step_raw(double *state, const double *u, const double *m0, const doub
                     int64_t n, int8_t *status, uint8_t *nattempts, void *stream);
 
 /* _compute_atarg's t_go (rocket_env.py:528-546): largest positive real root of
- * c0 t^4 + c2 t^2 + c3 t + c4, one per element (NaN when there is none). */
-int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo,
+ * c0 t^4 + c2 t^2 + c3 t + c4, one per element (NaN when there is none).  guess [n] nullable: per-element warm
+ * start of the iteration (the kernels pass the previous step's root), <= 0 = cold start. */
+int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, const double *guess, double *tgo,
            void *stream);
 
 /*

@@ -12,7 +12,7 @@ from .params import R6Params
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libr6dof.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 u8p = C.c_void_p
 
@@ -31,6 +31,7 @@ class R6Buffers(C.Structure):
         ("stats", C.c_void_p),
         ("scratch", C.c_void_p),
         ("work", C.c_void_p),
+        ("tgo", C.c_void_p),
     ]
 
 
@@ -93,7 +94,7 @@ def load(path: str | None = None):
                              C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.r6_sim_step_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
-    L.r6_tgo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]
+    L.r6_tgo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.r6_stats_reset.argtypes = [C.c_void_p, C.c_void_p]
     L.r6_step_random.argtypes = [pp, bp, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p]
     L.r6_step_range.argtypes = [pp, bp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_uint64, C.c_int64,

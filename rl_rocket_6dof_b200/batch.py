@@ -36,7 +36,8 @@ class Rocket6DOFBatch:
                  num_envs_global: Optional[int] = None, debug_buffers: bool = False, record_attempts: bool = False,
                  ic_table: Optional[np.ndarray] = None, params: Optional[EnvParams] = None,
                  precision: str = "fp64", reward_annealing: bool = False, vertical_attitude_reward=None,
-                 split_step: Optional[bool] = None, lanes: int = 1, multipass: Optional[bool] = None):
+                 split_step: Optional[bool] = None, lanes: int = 1, multipass: Optional[bool] = None,
+                 chunks: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("Rocket6DOFBatch needs a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
@@ -77,7 +78,8 @@ class Rocket6DOFBatch:
             self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.terminal_obs = torch.zeros(14, n, dtype=f32, device=dev)
             self.terminal_state = torch.zeros(14, n, dtype=sdt, device=dev)
-            self.ep_info = torch.zeros(2, n, dtype=f32, device=dev)
+            self.ep_info = torch.zeros(2, n, dtype=f64, device=dev)       # (return, length) of the finished episode
+            self.tgo = torch.zeros(n, dtype=f32, device=dev)              # warm start of the t_go root iteration
             self.stats = torch.zeros(8, dtype=f64, device=dev)
             # r6_step as two kernels (integrator | post-step) needs 2 bytes of device scratch per env; two launches
             # only pay off once the grid fills the machine several times over (measured cross-over: 2^16..2^17 envs)
@@ -94,8 +96,15 @@ class Rocket6DOFBatch:
                     raise ValueError("lanes must be <= min(num_envs, 32)")
                 split_step = True
                 self._lane_streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
-                base, rem = divmod(n, self.lanes)
-                self._lane_ranges = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(self.lanes)]
+                # `chunks` >= lanes contiguous env sub-ranges, dealt round-robin to the lane streams: a sub-range's
+                # kernels (integrator passes, post-step) follow each other on one stream while its state, work lists
+                # and outputs are still in L2 when the sub-range is small enough
+                self.chunks = self.lanes if chunks is None else int(chunks)
+                if self.chunks < self.lanes or self.chunks > 32 or self.chunks > n:
+                    raise ValueError("chunks must be in [lanes, min(num_envs, 32)]")
+                base, rem = divmod(n, self.chunks)
+                self._lane_ranges = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(self.chunks)]
+                self._lane_jobs = [(rg, self._lane_streams[r % self.lanes]) for r, rg in enumerate(self._lane_ranges)]
                 self._lane_fork = torch.cuda.Event()
             self._lanes_pending = False
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
@@ -139,6 +148,7 @@ class Rocket6DOFBatch:
         b.stats = ptr(self.stats)
         b.scratch = ptr(self.scratch)
         b.work = ptr(self.work)
+        b.tgo = ptr(self.tgo)
         return b
 
     def _stream(self) -> int:
@@ -157,7 +167,7 @@ class Rocket6DOFBatch:
                 if actions is not None:
                     actions.record_stream(st)
             for j in range(int(k)):
-                for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
+                for ln, ((first, count), st) in enumerate(self._lane_jobs):
                     _lib.check(self.lib.r6_step_range(C.byref(self._p), C.byref(self._b), self.num_envs, first, count, ln,
                                                       self.env_offset, ap, self.seed_value, self.steps_done + j,
                                                       st.cuda_stream), self.lib)
@@ -330,7 +340,7 @@ class Rocket6DOFBatch:
             for st in self._lane_streams:
                 st.wait_event(self._lane_fork)
             for j in range(int(k)):
-                for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
+                for ln, ((first, count), st) in enumerate(self._lane_jobs):
                     sl = slice(first, first + count)
                     with torch.cuda.stream(st):
                         obs[j, sl] = self.obs[:13, sl].t()
@@ -374,7 +384,7 @@ class Rocket6DOFBatch:
                 for st in self._lane_streams:
                     st.wait_event(self._lane_fork)
                 for j in range(int(k)):
-                    for ln, ((first, count), st) in enumerate(zip(self._lane_ranges, self._lane_streams)):
+                    for ln, ((first, count), st) in enumerate(self._lane_jobs):
                         _lib.check(L.r6_policy_range(C.byref(m), self.obs.data_ptr(), n, first, count, int(tensor_cores), 0,
                                                      self.seed_value, self.env_offset, self.steps_done + j, act.data_ptr(),
                                                      None, None, None, st.cuda_stream), L)
@@ -407,6 +417,7 @@ class Rocket6DOFBatch:
         self.v0[idx] = acc.to(torch.float32).sqrt()
         self.step_count[idx] = step_count
         self.ep_return[idx] = 0
+        self.tgo[idx] = 0
         self.obs[:, idx] = (self.state[:, idx].to(torch.float64) / torch.as_tensor(self.params.state_normalizer, device=self.device)[:, None]).to(torch.float32)
 
     def get_state(self) -> torch.Tensor:

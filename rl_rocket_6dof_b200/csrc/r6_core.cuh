@@ -42,16 +42,14 @@ R6_HD float f32_div(float a, float b) { return __fdiv_rn(a, b); }
 R6_HD float f32_sqrt(float a) { return __fsqrt_rn(a); }
 R6_HD float f32_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 R6_HD float f64_to_f32(double a) { return __double2float_rn(a); }
-// fast reciprocal / rsqrt: MUFU seed (2^-23) + two Newton steps => <= ~2 ulp, no IEEE special cases.
+// fast reciprocal / square root: MUFU seed (relative error 2^-20 measured on sm_100a, profiles/microbench/mufu_seed.cu)
+// + one third-order step r (1 + e + e^2), e = 1 - x r  =>  <= 1 ulp, three dependent FMAs, no IEEE special cases.
 R6_HD double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 // one Newton step only (~1e-12 relative): for the tolerance-scaled norms of the step-size controller,
 // where 1e-12 in a scale moves the next step size by 1e-12 and the solution by < 1e-15
@@ -64,17 +62,16 @@ R6_HD double fast_rcp1(double x)
 R6_HD double fast_sqrt(double x)
 {
     double r;
-    // seed on max(x, tiny): x = 0 then gives s = 0 * r = 0 without a branch
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(fmax(x, 1e-300)));
-    // Newton on y = 1/sqrt(x): y <- y + y*(0.5 - 0.5*x*y*y)
-    double hx = 0.5 * x;
-    double e = fma(-hx * r, r, 0.5);
-    r = fma(r, e, r);
-    e = fma(-hx * r, r, 0.5);
-    r = fma(r, e, r);
-    double s = x * r;                       // sqrt(x) ~ x * rsqrt(x)
-    double d = fma(-s, s, x);               // one correction step on the square root itself
-    return fma(d, 0.5 * r, s);
+    // seed on x + tiny: x = 0 then gives s = 0 * r = 0 without a branch (x + 1e-300 == x for every normal x)
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x + 1e-300));
+    // coupled (Goldschmidt) iteration on s ~ sqrt(x), h ~ 1/(2 sqrt(x)): two quadratic steps 2^-20 -> 2^-40 -> 2^-80,
+    // i.e. rounding-limited (<= 1 ulp measured); 2 DMUL + 5 DFMA
+    double s = x * r, h = 0.5 * r;
+    double e = fma(-s, h, 0.5);
+    s = fma(s, e, s);
+    h = fma(h, e, h);
+    e = fma(-s, h, 0.5);
+    return fma(s, e, s);
 }
 #else
 R6_HD float f32_mul(float a, float b) { return a * b; }
@@ -281,6 +278,10 @@ struct StepConstT {
     R dm;              // mass rate (simulator.py:140-141)
     // air-density expansion around the step's initial height (simulator.py:145-150)
     R h0, rho0, kd;    // rho(h) = rho0 * (1 - d)^p, d = kd*(h - h0), p = -(1 + g0 M / R / L)
+    // folded forms consumed by rhs() (set by consts_finish / density_setup):
+    R hw0;             // w0 / 2                              (quaternion kinematics)
+    R j5, k1, k2;      // 5 Ji1, 20 Ji1 Tb2, -20 Ji1 Tb1      (torques written on the total force F = Tb + A)
+    R nkdh0, rhoc;     // -kd h0, -S_ref C_a rho0 / 2         (d = kd h + nkdh0; aero factor = rhoc (1 - d)^p)
 };
 using StepConst = StepConstT<double>;
 
@@ -293,6 +294,7 @@ constexpr double kSref = 3.14159265358979323846 * kRb2;
 constexpr double kRhoExp = 1 + 9.81 * 0.0289644 / 8.3144598 / (-0.0065);   // ~ -4.2559
 constexpr double kLapseOverT = 0.0065 / 288.15;
 constexpr double kCa = 0.82;
+constexpr double kAero = -0.5 * kSref * kCa;     // aerodynamic force = kAero rho |v| v_body (simulator.py:216-219)
 
 // x^e for x > 0 (one call per env-step: the density at the step's initial height)
 R6_HD_NOINLINE double pow_pos(double x, double e) { return exp(e * log(x)); }
@@ -342,6 +344,8 @@ R6_HD void density_setup(StepConstT<R> &c, R h0)
     } else {
         c.rho0 = R(1.225) * pow_pos(base, R(-kRhoExp));
     }
+    c.nkdh0 = -(c.kd * h0);
+    c.rhoc = R(kAero) * c.rho0;
 }
 
 // kExact = false: binomial series of (1 - d)^p around the step's initial height, d = kd (h - h0),
@@ -386,6 +390,16 @@ R6_HD R density(const StepConstT<R> &c, R h)
 }
 constexpr double kMaxDtSeries = 0.25;   // (1000 m/s + 60 m/s^2 dt) dt kd <= 0.01 up to here
 
+// folded per-step constants of rhs() from (Tb, Ji1, w0)
+template <class R>
+R6_HD void consts_finish(StepConstT<R> &c, R w0)
+{
+    c.hw0 = R(0.5) * w0;
+    c.j5 = R(5.0) * c.Ji1;
+    c.k1 = R(20.0) * c.Ji1 * c.Tb2;
+    c.k2 = R(-20.0) * c.Ji1 * c.Tb1;
+}
+
 // env mode constants from the float32 control / initial mass
 template <class R>
 R6_HD void consts_env_mode(StepConstT<R> &c, float m0, float u0, float u1, float u2, R w0)
@@ -402,6 +416,7 @@ R6_HD void consts_env_mode(StepConstT<R> &c, float m0, float u0, float u1, float
     c.Tb1 = (R)f32_mul(sy, cz) * T;
     c.Tb2 = (R)sz * T;
     c.dm = (R)f32_div(-u2, (float)(9.81 * 360));
+    consts_finish(c, w0);
 }
 // raw Simulator6DOF mode: python-list inputs => everything float64 (test_6DOF_simulator.py)
 R6_HD void consts_raw_mode(StepConst &c, double m0, double u0, double u1, double u2, double w0)
@@ -414,6 +429,7 @@ R6_HD void consts_raw_mode(StepConst &c, double m0, double u0, double u1, double
     c.Tb1 = (sy * cz) * u2;
     c.Tb2 = sz * u2;
     c.dm = -u2 / (9.81 * 360);
+    consts_finish(c, w0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -443,35 +459,60 @@ R6_HD RotUT<R> rot_unnormalised(R q0, R q1, R q2, R q3)
     return r;
 }
 
-// simulator.py:106-143 — inputs: height, velocity, quaternion, (w1,w2), mass of the stage state
+// simulator.py:106-143 — inputs: height, velocity, quaternion, (w1,w2), mass of the stage state.
+// Written for the FP64 pipe (89 instructions, 2/3 of them FMAs):
+//   * rotation matrix from the doubled quaternion components and two sums / differences of squares
+//     (M = |q|^2 R; 22 operations instead of 34);
+//   * the constant factors of the drag (-S C_a / 2) ride on the density constant rhoc, the 1/2 of the quaternion
+//     kinematics on the body rates;
+//   * torques on the total body force F = Tb + A:  tau_y = 15 Tb2 - 5 A2 = 20 Tb2 - 5 F2 (the subtraction F - Tb that
+//     this hides costs < 1e-16 rad/s^2), so A itself is never formed and F comes out of three FMAs.
 template <bool kExact, class R>
-R6_HD DerivT<R> rhs(const StepConstT<R> &c, R w0, R h, R v0, R v1, R v2, R q0, R q1, R q2, R q3, R w1, R w2, R m)
+R6_HD DerivT<R> rhs(const StepConstT<R> &c, R h, R v0, R v1, R v2, R q0, R q1, R q2, R q3, R w1, R w2, R m)
 {
     DerivT<R> d;
-    const R rho = density<kExact>(c, h);
-    const RotUT<R> M = rot_unnormalised(q0, q1, q2, q3);
-    const R inv = fast_rcp(M.n2 * m);       // 1 / (|q|^2 m)
+    R rhoS;                                  // -S_ref C_a rho(h) / 2
+    if (kExact) rhoS = R(kAero) * density_exact(h);
+    else {
+        const R dd = fma(c.kd, h, c.nkdh0);
+        // float: d^4 and beyond are below the rounding of the sum (|d| <= 0.01)
+        R s = (sizeof(R) == 8) ? fma(fma(fma(rho_b(6, R()), dd, rho_b(5, R())), dd, rho_b(4, R())), dd, rho_b(3, R())) : rho_b(3, R());
+        s = fma(s, dd, rho_b(2, R()));
+        s = fma(s, dd, rho_b(1, R()));
+        s = fma(s, dd, R(1.0));
+        rhoS = c.rhoc * s;
+    }
+    // un-normalised rotation matrix M = |q|^2 R(q), leading-scalar quaternion (simulator.py:177-186)
+    const R Q1 = q1 + q1, Q2 = q2 + q2, Q3 = q3 + q3;
+    const R ww = q0 * q0, zz = q3 * q3;
+    const R s1 = fma(q1, q1, ww), s2 = fma(q2, q2, zz), d1 = fma(-q1, q1, ww), d2 = fma(q2, q2, -zz);
+    const R n2 = s1 + s2, m00 = s1 - s2, m11 = d1 + d2, m22 = d1 - d2;
+    const R zw = Q3 * q0, yw = Q2 * q0, xw = Q1 * q0;
+    const R m01 = fma(Q1, q2, -zw), m10 = fma(Q1, q2, zw);
+    const R m02 = fma(Q1, q3, yw), m20 = fma(Q1, q3, -yw);
+    const R m12 = fma(Q2, q3, -xw), m21 = fma(Q2, q3, xw);
+    const R inv = fast_rcp(n2 * m);          // 1 / (|q|^2 m)
     const R inv_n2 = inv * m;
     // body-frame velocity (R^T v) and aerodynamic force (simulator.py:216-219)
-    const R vb0 = M.m00 * v0 + M.m10 * v1 + M.m20 * v2;
-    const R vb1 = M.m01 * v0 + M.m11 * v1 + M.m21 * v2;
-    const R vb2 = M.m02 * v0 + M.m12 * v1 + M.m22 * v2;
-    const R vn = fast_sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-    const R ca = (((R(-0.5) * rho) * vn) * R(kSref)) * R(kCa) * inv_n2;
-    const R A0 = ca * vb0, A1 = ca * vb1, A2 = ca * vb2;
-    const R F0 = c.Tb0 + A0, F1 = c.Tb1 + A1, F2 = c.Tb2 + A2;
+    const R vb0 = fma(m20, v2, fma(m10, v1, m00 * v0));
+    const R vb1 = fma(m21, v2, fma(m11, v1, m01 * v0));
+    const R vb2 = fma(m22, v2, fma(m12, v1, m02 * v0));
+    const R vn = fast_sqrt(fma(v2, v2, fma(v1, v1, v0 * v0)));
+    const R ca = rhoS * vn * inv_n2;
+    const R F0 = fma(ca, vb0, c.Tb0), F1 = fma(ca, vb1, c.Tb1), F2 = fma(ca, vb2, c.Tb2);
     // simulator.py:127-130, 156-165
-    d.dv0 = (M.m00 * F0 + M.m01 * F1 + M.m02 * F2) * inv - R(kG0);
-    d.dv1 = (M.m10 * F0 + M.m11 * F1 + M.m12 * F2) * inv;
-    d.dv2 = (M.m20 * F0 + M.m21 * F1 + M.m22 * F2) * inv;
+    d.dv0 = fma(fma(m02, F2, fma(m01, F1, m00 * F0)), inv, R(-kG0));
+    d.dv1 = fma(m12, F2, fma(m11, F1, m10 * F0)) * inv;
+    d.dv2 = fma(m22, F2, fma(m21, F1, m20 * F0)) * inv;
     // simulator.py:136, 221-229 (un-normalised quaternion)
-    d.dq0 = R(0.5) * (-w0 * q1 - w1 * q2 - w2 * q3);
-    d.dq1 = R(0.5) * (w0 * q0 + w2 * q2 - w1 * q3);
-    d.dq2 = R(0.5) * (w1 * q0 - w2 * q1 + w0 * q3);
-    d.dq3 = R(0.5) * (w2 * q0 + w1 * q1 - w0 * q2);
+    const R hw0 = c.hw0, hw1 = R(0.5) * w1, hw2 = R(0.5) * w2;
+    d.dq0 = fma(-hw0, q1, fma(-hw1, q2, -(hw2 * q3)));
+    d.dq1 = fma(hw0, q0, fma(hw2, q2, -(hw1 * q3)));
+    d.dq2 = fma(hw1, q0, fma(-hw2, q1, hw0 * q3));
+    d.dq3 = fma(hw2, q0, fma(hw1, q1, -(hw0 * q2)));
     // simulator.py:137, 232-244: tau = [0, 15 T2 - 5 A2, -15 T1 + 5 A1];  J = diag(J0, J1, J1)
-    d.dw1 = c.Ji1 * (15 * c.Tb2 - 5 * A2) - c.gy * w2;
-    d.dw2 = c.Ji1 * (-15 * c.Tb1 + 5 * A1) + c.gy * w1;
+    d.dw1 = fma(-c.gy, w2, fma(-c.j5, F2, c.k1));
+    d.dw2 = fma(c.gy, w1, fma(c.j5, F1, c.k2));
     return d;
 }
 
@@ -498,8 +539,13 @@ using KLocal = KLocalT<double>;
 template <class R, int kThreadsPerBlock>
 struct KShared {
     R *base;   // smem + threadIdx.x
+#ifdef R6_FAKE_STAGES     /* TIMING EXPERIMENT ONLY (wrong results): fewer stage slots => more resident CTAs */
+    __device__ __forceinline__ R get(int j, int c) const { return base[((j < R6_FAKE_STAGES ? j : R6_FAKE_STAGES - 1) * kNK + c) * kThreadsPerBlock]; }
+    __device__ __forceinline__ void set(int j, int c, R v) { base[((j < R6_FAKE_STAGES ? j : R6_FAKE_STAGES - 1) * kNK + c) * kThreadsPerBlock] = v; }
+#else
     __device__ __forceinline__ R get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
     __device__ __forceinline__ void set(int j, int c, R v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
+#endif
 };
 #endif
 template <class KS, class R>
@@ -639,6 +685,54 @@ R6_HD float inv_root5(float x)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Evaluation point of one right-hand-side call: x = y + h sum_j SA[ROW][j] K_j (rk_step, rk.py:58-66), positions from
+// the squared tableau.  One instantiation per row of the extended tableau, fully unrolled: the coefficients are
+// constant-bank operands of the FMAs at fixed offsets, the stage loads are all issued up front, and only the height is
+// formed for the stage rows (the horizontal positions enter nothing but y_new, row 6).  B[1] = 0: row 6 reads the
+// velocity components of stage 1 only (for the position sums).
+template <class R>
+struct EvalPoint {
+    R h, r1, r2, v0, v1, v2, q0, q1, q2, q3, w1, w2, m;
+};
+template <int ROW, class KS, class R>
+R6_HD void stage_point(const KS &K, const R *y, R hh, R dm, EvalPoint<R> &x)
+{
+    const TabT<R> &T = tab<R>();
+    constexpr int cnt = ROW < 6 ? ROW : (ROW == 6 ? 6 : 1);
+    constexpr bool kHoriz = ROW == 6;            // horizontal positions only for y_new
+    constexpr bool kPos = ROW != 7;              // row 7 (probe) has no h^2 term
+    R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
+#pragma unroll
+    for (int j = 0; j < cnt; j++) {
+        const bool skip_a = (ROW == 6 && j == 1);
+        const R a = T.SA[ROW][j], aa = T.SAA[ROW][j];
+        const R k0 = K.get(j, 0);
+        // j = 0 starts the sums with a product (no zeroed accumulators); SAA[ROW][0] = 0 only for ROW = 1 and 7
+        if (!skip_a) acc[0] = j == 0 ? a * k0 : fma(a, k0, acc[0]);
+        if (kPos) ar0 = j == 0 ? aa * k0 : fma(aa, k0, ar0);
+        if (!skip_a || kHoriz) {
+            const R k1 = K.get(j, 1), k2 = K.get(j, 2);
+            if (!skip_a) { acc[1] = j == 0 ? a * k1 : fma(a, k1, acc[1]); acc[2] = j == 0 ? a * k2 : fma(a, k2, acc[2]); }
+            if (kHoriz) { ar1 = j == 0 ? aa * k1 : fma(aa, k1, ar1); ar2 = j == 0 ? aa * k2 : fma(aa, k2, ar2); }
+        }
+        if (!skip_a) {
+#pragma unroll
+            for (int i = 3; i < kNK; i++) acc[i] = j == 0 ? a * K.get(j, i) : fma(a, K.get(j, i), acc[i]);
+        }
+    }
+    const R hc = hh * T.SC[ROW], hh2 = hh * hh;
+    x.h = kPos ? fma(hh2, ar0, fma(hc, y[3], y[0])) : fma(hc, y[3], y[0]);
+    if (kHoriz) {
+        x.r1 = fma(hh2, ar1, fma(hc, y[4], y[1]));
+        x.r2 = fma(hh2, ar2, fma(hc, y[5], y[2]));
+    }
+    x.v0 = fma(hh, acc[0], y[3]); x.v1 = fma(hh, acc[1], y[4]); x.v2 = fma(hh, acc[2], y[5]);
+    x.q0 = fma(hh, acc[3], y[6]); x.q1 = fma(hh, acc[4], y[7]); x.q2 = fma(hh, acc[5], y[8]); x.q3 = fma(hh, acc[6], y[9]);
+    x.w1 = fma(hh, acc[7], y[11]); x.w2 = fma(hh, acc[8], y[12]);
+    x.m = fma(hc, dm, y[13]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // solve_ivp(fun, [t, t+dt], y, events=height) with all defaults.  y in/out (quaternion NOT yet
 // re-normalised).  Returns the scipy status (0 / 1 / -1); natt = accepted + rejected RK attempts.
 //
@@ -661,8 +755,11 @@ struct PassCtx {
     int natt, budget;
     bool rejected;
 };
+#ifndef R6_ROWS_UNROLLED
+#define R6_ROWS_UNROLLED 1      /* 1: stage_point<ROW> per row (switch); 0: one rolled loop with constant-bank indexing */
+#endif
 template <bool kExact, class KS, class R, int kPass = 0>
-R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx<R> *px = nullptr)
+R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx<R> &px)
 {
     const TabT<R> &T = tab<R>();
     constexpr R rtol = R(1e-3), atol = R(1e-6);
@@ -670,12 +767,10 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     constexpr int kStageF0 = -1, kStageProbe = 0;        // stage >= 1: Dormand-Prince stage index (6 = f(y_new))
     const R t_bound = t + dt;
     const R L = fabs(t_bound - t);                       // common.py:100 (interval length as SciPy computes it)
-    const R w0 = y[10];
-    if constexpr (kPass == 2) density_setup(c, px->h_ref);
+    if constexpr (kPass == 2) density_setup(c, px.h_ref);
     else density_setup(c, y[0]);
     // evaluation point (height, v, q, w1, w2, m) + the two horizontal positions of y_new
-    R xh = y[0], xv0 = y[3], xv1 = y[4], xv2 = y[5], xq0 = y[6], xq1 = y[7], xq2 = y[8], xq3 = y[9];
-    R xw1 = y[11], xw2 = y[12], xm = y[13], xr1 = y[1], xr2 = y[2];
+    EvalPoint<R> x = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]};
     int stage = kStageF0;
     R h = 0, h_abs = 0, t_new = t;
     R g = y[0];
@@ -683,11 +778,11 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     bool rejected = false;
     natt = 0;
     int budget = 0;
-    if constexpr (kPass != 0) budget = px->budget;
-    if constexpr (kPass == 1) px->h_ref = y[0];
-    if constexpr (kPass == 2) { t = px->t; t_new = t; h_abs = px->h_abs; rejected = px->rejected; natt = px->natt; }
+    if constexpr (kPass != 0) budget = px.budget;
+    if constexpr (kPass == 1) px.h_ref = y[0];
+    if constexpr (kPass == 2) { t = px.t; t_new = t; h_abs = px.h_abs; rejected = px.rejected; natt = px.natt; }
     for (;;) {
-        const DerivT<R> d = rhs<kExact>(c, w0, xh, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2, xm);
+        const DerivT<R> d = rhs<kExact>(c, x.h, x.v0, x.v1, x.v2, x.q0, x.q1, x.q2, x.q3, x.w1, x.w2, x.m);
         bool begin_attempt = false;
         int row;
         R hh;
@@ -702,30 +797,36 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             for (int i = 0; i < kNK; i++) es[i] = 0;
 #pragma unroll
             for (int i = 0; i < 3; i++) er[i] = 0;
+#if R6_ROWS_UNROLLED
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int j = 0; j < 6; j++) {
                 const R e = T.E[j], ea = T.EA[j];
 #pragma unroll
                 for (int i = 0; i < kNK; i++) {
+                    if (R6_ROWS_UNROLLED && j == 1 && i >= 3) continue;       // E[1] = 0: only EA[1] K_1[0..2] counts
                     const R k = K.get(j, i);
-                    es[i] = fma(e, k, es[i]);
+                    if (!(R6_ROWS_UNROLLED && j == 1)) es[i] = fma(e, k, es[i]);
                     if (i < 3) er[i] = fma(ea, k, er[i]);
                 }
             }
             const R e6 = T.E[6];
             const R fnv[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
             const R yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
-            const R yw[12] = {xh, xr1, xr2, xv0, xv1, xv2, xq0, xq1, xq2, xq3, xw1, xw2};
-            const R h2 = h * h;
-            // the w0 and mass rows contribute exactly 0 to the error norm
-            R ssum = 0;
+            const R yw[12] = {x.h, x.r1, x.r2, x.v0, x.v1, x.v2, x.q0, x.q1, x.q2, x.q3, x.w1, x.w2};
+            // err^2 14 = sum_i (e_i / sc_i)^2 with e_i = h^2 er_i (positions), h (es_i + E6 fn_i) (the rest): the powers of
+            // h are factored out of the sums; the w0 and mass rows contribute exactly 0 to the error norm
+            R sr = 0, so = 0;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                const R sc = fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol);
-                const R e = (i < 3) ? h2 * er[i] : h * fma(e6, fnv[i - 3], es[i - 3]);
-                ssum += sq(e * fast_rcp1(sc));
+                const R isc = fast_rcp1(fma(fmax(fabs(yo[i]), fabs(yw[i])), rtol, atol));
+                const R q = (i < 3 ? er[i] : fma(e6, fnv[i < 3 ? 0 : i - 3], es[i < 3 ? 0 : i - 3])) * isc;
+                if (i < 3) sr = fma(q, q, sr);
+                else so = fma(q, q, so);
             }
-            const R err = fast_sqrt(ssum) * inv_sqrt14;
+            const R err = fabs(h) * fast_sqrt(fma(h * h, sr, so)) * inv_sqrt14;
             const R raw = (err == 0) ? R(10.0) : R(0.9) * inv_root5(err);        // SAFETY * err^(-1/5)
             if (err < 1) {
                 R factor = fmin(R(10.0), raw);
@@ -733,16 +834,17 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
                 h_abs *= factor;
                 // accepted: ivp.py:659-699
                 const R t_old = t;
-                const R g_new = xh;
+                const R g_new = x.h;
                 const bool ev = (g <= 0 && g_new >= 0) || (g >= 0 && g_new <= 0);
                 t = t_new;
                 if (t - t_bound >= 0) status = 0;
                 if (ev) {
-                    event_resolve(c, y, K, d, t_old, t_new);
+                    const DerivT<R> fn = d;                         // the address-taken copy exists on this rare path only
+                    event_resolve(c, y, K, fn, t_old, t_new);
                     status = 1;
                 } else {
-                    y[0] = xh; y[1] = xr1; y[2] = xr2; y[3] = xv0; y[4] = xv1; y[5] = xv2;
-                    y[6] = xq0; y[7] = xq1; y[8] = xq2; y[9] = xq3; y[11] = xw1; y[12] = xw2; y[13] = xm;
+                    y[0] = x.h; y[1] = x.r1; y[2] = x.r2; y[3] = x.v0; y[4] = x.v1; y[5] = x.v2;
+                    y[6] = x.q0; y[7] = x.q1; y[8] = x.q2; y[9] = x.q3; y[11] = x.w1; y[12] = x.w2; y[13] = x.m;
                 }
                 if (status != -2) break;
                 k_store(K, 0, d);                                   // first-same-as-last
@@ -754,7 +856,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             }
             if constexpr (kPass != 0) {
                 if (--budget == 0) {                                // hand the env to the next pass
-                    px->t = t; px->h_abs = h_abs; px->rejected = rejected; px->natt = natt;
+                    px.t = t; px.h_abs = h_abs; px.rejected = rejected; px.natt = natt;
                     break;
                 }
             }
@@ -771,7 +873,10 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             for (int i = 0; i < 14; i++) {
                 const R isc = fast_rcp1(fma(fabs(y[i]), rtol, atol));
                 s0 += sq(y[i] * isc);
-                s1 += sq(fv[i] * isc);
+                if (i != 10) s1 += sq(fv[i] * isc);
+                // the 12 scales the probe needs again (all rows but w0 and the mass) wait in the still unused slots of
+                // stages 1 and 2
+                if (i != 10 && i != 13) { const int s = i < 10 ? i : i - 1; K.set(1 + s / kNK, s % kNK, isc); }
             }
             const R d0 = fast_sqrt(s0) * inv_sqrt14, d1 = fast_sqrt(s1) * inv_sqrt14;
             R h0 = (d0 < R(1e-5) || d1 < R(1e-5)) ? R(1e-6) : R(0.01) * d0 * fast_rcp(d1);
@@ -784,18 +889,16 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             // ---- d = f(y + h0 f0); select_initial_step part 2 (common.py:121-134) ----
             const R h0 = h, d1 = h_abs;
             // (f1 - f0)/scale: position rows are h0*dv, the w0 and mass rows are 0
-            const R f0v[kNK] = {K.get(0, 0), K.get(0, 1), K.get(0, 2), K.get(0, 3), K.get(0, 4), K.get(0, 5),
-                                K.get(0, 6), K.get(0, 7), K.get(0, 8)};
             const R f1v[kNK] = {d.dv0, d.dv1, d.dv2, d.dq0, d.dq1, d.dq2, d.dq3, d.dw1, d.dw2};
-            const R yo[12] = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12]};
-            R s2 = 0;
+            R sp = 0, so = 0;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                const R isc = fast_rcp1(fma(fabs(yo[i]), rtol, atol));
-                const R e = (i < 3) ? h0 * f0v[i] : f1v[i - 3] - f0v[i - 3];
-                s2 += sq(e * isc);
+                const R isc = K.get(1 + i / kNK, i % kNK);
+                const R q = (i < 3 ? K.get(0, i) : f1v[i < 3 ? 0 : i - 3] - K.get(0, i < 3 ? 0 : i - 3)) * isc;
+                if (i < 3) sp = fma(q, q, sp);
+                else so = fma(q, q, so);
             }
-            const R d2 = fast_sqrt(s2) * inv_sqrt14 * fast_rcp(h0);
+            const R d2 = fast_sqrt(fma(h0 * h0, sp, so)) * inv_sqrt14 * fast_rcp(h0);
             const R tiny15 = R(1e-15);
             const R h1 = (d1 <= tiny15 && d2 <= tiny15) ? fmax(R(1e-6), h0 * R(1e-3)) : inv_root5(R(100.0) * fmax(d1, d2));
             h_abs = fmin(fmin(100 * h0, h1), L);
@@ -817,6 +920,17 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             row = 1; hh = h;
         }
         // ---- evaluation point of the next RHS call: rk_step (rk.py:58-66) with the row's coefficients ----
+#if R6_ROWS_UNROLLED
+        switch (row) {
+        case 1: stage_point<1>(K, y, hh, c.dm, x); break;
+        case 2: stage_point<2>(K, y, hh, c.dm, x); break;
+        case 3: stage_point<3>(K, y, hh, c.dm, x); break;
+        case 4: stage_point<4>(K, y, hh, c.dm, x); break;
+        case 5: stage_point<5>(K, y, hh, c.dm, x); break;
+        case 6: stage_point<6>(K, y, hh, c.dm, x); break;
+        default: stage_point<7>(K, y, hh, c.dm, x); break;
+        }
+#else
         {
             R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
 #pragma unroll
@@ -832,16 +946,25 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
                 for (int i = 3; i < kNK; i++) acc[i] = fma(a, K.get(j, i), acc[i]);
             }
             const R hc = hh * T.SC[row], hh2 = hh * hh;
-            xh = fma(hh2, ar0, fma(hc, y[3], y[0]));
-            xr1 = fma(hh2, ar1, fma(hc, y[4], y[1]));
-            xr2 = fma(hh2, ar2, fma(hc, y[5], y[2]));
-            xv0 = fma(hh, acc[0], y[3]); xv1 = fma(hh, acc[1], y[4]); xv2 = fma(hh, acc[2], y[5]);
-            xq0 = fma(hh, acc[3], y[6]); xq1 = fma(hh, acc[4], y[7]); xq2 = fma(hh, acc[5], y[8]); xq3 = fma(hh, acc[6], y[9]);
-            xw1 = fma(hh, acc[7], y[11]); xw2 = fma(hh, acc[8], y[12]);
-            xm = fma(hc, c.dm, y[13]);
+            x.h = fma(hh2, ar0, fma(hc, y[3], y[0]));
+            x.r1 = fma(hh2, ar1, fma(hc, y[4], y[1]));
+            x.r2 = fma(hh2, ar2, fma(hc, y[5], y[2]));
+            x.v0 = fma(hh, acc[0], y[3]); x.v1 = fma(hh, acc[1], y[4]); x.v2 = fma(hh, acc[2], y[5]);
+            x.q0 = fma(hh, acc[3], y[6]); x.q1 = fma(hh, acc[4], y[7]); x.q2 = fma(hh, acc[5], y[8]); x.q3 = fma(hh, acc[6], y[9]);
+            x.w1 = fma(hh, acc[7], y[11]); x.w2 = fma(hh, acc[8], y[12]);
+            x.m = fma(hc, c.dm, y[13]);
         }
+#endif
     }
     return status;
+}
+
+// the single-call form (kPass = 0)
+template <bool kExact, class KS, class R>
+R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K)
+{
+    PassCtx<R> px{};
+    return integrate<kExact, KS, R, 0>(c, y, t, dt, natt, K, px);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -866,18 +989,61 @@ R6_HD W quartic_df(W c0, W c2, W c3, W t)
 {
     return fma(fma(4 * c0, t * t, 2 * c2), t, c3);
 }
+// `guess` (optional warm start, 0 = none): the root found for the same env one step earlier.  t_go moves by about dt
+// per env-step, so Newton from the previous root needs 3-4 steps instead of the ~10 + 3 of the cold start from the
+// Fujiwara bound.  A warm result is accepted only when it is CERTIFIED to be the largest positive root:
+//   (A) f(t_i) <= 0 (or no inflection point): the largest root is the only root right of t_i, where f is convex and
+//       tends to +inf — any converged iterate x > t_i with f'(x) > 0 is it;
+//   (B) f(t_i) > 0 and f'(t_i) >= 0: f' has its minimum at t_i, so f increases on all of t > 0 and has exactly one
+//       positive root, inside (0, t_i) — any converged iterate there is it.
+// Anything else — the third sign pattern (a local minimum right of t_i decides), an iterate leaving the interval, a
+// non-positive slope, no convergence in 6 steps — falls back to the cold start below.
 template <class W>
-R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4)
+R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4, W guess = W(0))
 {
     if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return W(NAN);       // no sign change => no positive root
-    // Fujiwara bound on the root moduli; float32 is plenty for a bound (inflated by 1e-4)
     const W ic0 = fast_rcp(c0);
+    const W ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * W(1.0 / 6)) : W(0.0);
+    if (guess > 0) {
+        W lo = ti, hi = W(INFINITY);                              // case (A)
+        bool usable = true;
+        if (ti > 0) {
+            const W fi = quartic_f(c0, c2, c3, c4, ti);
+            if (fi > 0) {
+                if (quartic_df(c0, c2, c3, ti) >= 0) { lo = 0; hi = ti; }      // case (B)
+                else usable = false;
+            }
+        }
+        W x = fmin(guess, hi);
+        if (usable && x > lo) {
+            W fx = quartic_f(c0, c2, c3, c4, x), dx = x;
+            bool conv = false;
+#pragma unroll 1
+            for (int it = 0; it < 6; it++) {
+                const W dfx = quartic_df(c0, c2, c3, x);
+                if (!(dfx > 0)) break;
+                dx = fx * fast_rcp(dfx);
+                x -= dx;
+                if (!(x > lo && x <= hi)) break;
+                fx = quartic_f(c0, c2, c3, c4, x);
+                // quadratic convergence: a correction below 1e-8 x leaves an error of ~1e-16 x
+                if (fabs(dx) <= W(sizeof(W) == 8 ? 1e-8 : 1e-4) * x) { conv = true; break; }
+            }
+            if (conv) {
+                const W dfx = quartic_df(c0, c2, c3, x);
+                if (dfx > 0) {
+                    const W xn = x - fx * fast_rcp(dfx);          // polish: rounding level
+                    if (xn > lo && xn <= hi) return xn;
+                }
+            }
+        }
+    }
+    // Fujiwara bound on the root moduli; float32 is plenty for a bound (inflated by 1e-4)
     const float a2 = (float)(fabs(c2) * ic0), a1 = (float)(fabs(c3) * ic0), a0 = (float)(fabs(c4) * ic0);
     const W B = (W)(2.0002f * fmaxf(sqrtf(a2), fmaxf(cbrtf(a1), sqrtf(sqrtf(0.5f * a0)))));
     if (!(B > 0) || !isfinite(B)) return W(NAN);
     W lo = 0, hi = B;
     bool from_right = true;
-    const W ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * W(1.0 / 6)) : W(0.0);
     if (ti > 0 && ti < B) {
         const W fi = quartic_f(c0, c2, c3, c4, ti);
         if (fi <= 0) { lo = ti; }
@@ -1079,6 +1245,7 @@ struct PostOut {
     double terms[R6_NTERMS];
     uint32_t flags;       // R6_F_* (EVENT, OOB and the five landing flags)
     bool tgo_missing;
+    float tgo;            // the t_go root of this step (warm start of the next step's iteration), 0 when there is none
 };
 
 // rocket_env.py:206-231 after the simulator step.  S = post-step state with the quaternion already
@@ -1092,7 +1259,7 @@ R6_HD double w_exp(double x) { return exp(x); }
 R6_HD float w_exp(float x) { return expf(x); }
 template <class RS, class W>
 R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<RS> &cr, const W *S, float u2,
-                     float v0_episode, int status, PostOut &o)
+                     float v0_episode, int status, PostOut &o, float tgo_guess = 0.0f)
 {
     struct { W Tb0, Tb1, Tb2; } c = {(W)cr.Tb0, (W)cr.Tb1, (W)cr.Tb2};
     float s[14];
@@ -1107,15 +1274,22 @@ R6_HD void post_step(const R6Params &p, const AngleTests &at, const StepConstT<R
     euler_limit_tests(at, (W)s[6], (W)s[7], (W)s[8], (W)s[9], att_viol, att_land);
     W shaping;
     o.tgo_missing = false;
+    o.tgo = 0.0f;
     if (!p.shaping_velocity) {
         // _compute_atarg (:526-566)
         const W c0 = W((-9.81) * (-9.81));
         const float c2 = f32_mul(-4.0f, f32_mul(vn, vn));
         const float c3 = f32_mul(-24.0f, sdot3(s[0], s[1], s[2], s[3], s[4], s[5]));
         const float c4 = f32_mul(-36.0f, f32_mul(rn, rn));
-        const W tgo = tgo_largest_root(c0, (W)c2, (W)c3, (W)c4);
+        W tgo = tgo_largest_root(c0, (W)c2, (W)c3, (W)c4, (W)tgo_guess);
+        // no positive real root (the reference raises IndexError at rocket_env.py:545): cannot happen for r != 0 (the
+        // quartic is negative at 0 and positive at infinity); for r = 0 exactly the target acceleration is defined as
+        // that of t_go -> infinity (a_targ = -g), which keeps the reward finite instead of poisoning the statistics
         o.tgo_missing = !(tgo > 0);
-        const W itg = fast_rcp(tgo), itg2 = itg * itg;
+        W itg = fast_rcp(tgo);
+        if (o.tgo_missing) itg = W(0.0);
+        else o.tgo = to_f32(tgo);
+        const W itg2 = itg * itg;
         const W q0 = (W)f32_mul(-6.0f, s[0]) * itg2 - (W)f32_mul(4.0f, s[3]) * itg + W(9.81);
         const W q1 = (W)f32_mul(-6.0f, s[1]) * itg2 - (W)f32_mul(4.0f, s[4]) * itg;
         const W q2 = (W)f32_mul(-6.0f, s[2]) * itg2 - (W)f32_mul(4.0f, s[5]) * itg;
@@ -1400,6 +1574,7 @@ struct EnvT {
     int k;             // steps taken in the episode
     uint32_t episode;  // episodes started so far (RNG counter)
     double ep_return;
+    float tgo;         // t_go root of the previous step (0 = none): warm start of tgo_largest_root
 };
 using Env = EnvT<double>;
 
@@ -1423,6 +1598,7 @@ R6_HD void env_reset(const R6Params &p, const R6Buffers &b, uint64_t seed, int64
     e.k = 0;
     e.episode += 1;
     e.ep_return = 0.0;
+    e.tgo = 0.0f;
 }
 
 struct StepOut {
@@ -1479,7 +1655,7 @@ R6_HD int env_integrate_pass(const R6Params &p, const double *__restrict__ t_tab
         const int kk = k < p.n_t ? k : p.n_t - 1;
         t = (R)t_table[kk];
     }
-    const int status = integrate<kExact, KS, R, kPass>(c, y, t, (R)p.dt, natt, K, &px);
+    const int status = integrate<kExact, KS, R, kPass>(c, y, t, (R)p.dt, natt, K, px);
     if (status != -2) normalize_quat(y);
     return status;
 }
@@ -1497,7 +1673,8 @@ R6_HD void env_post(const R6Params &p, const Derived &dv, EnvT<R> &e, float a0, 
     o.status = status;
     o.natt = natt;
     e.k += 1;
-    post_step(p, dv.at, c, e.y, u2, e.v0, o.status, o.post);      // working precision = R
+    post_step(p, dv.at, c, e.y, u2, e.v0, o.status, o.post, e.tgo);      // working precision = R
+    e.tgo = o.post.tgo;
     uint32_t fl = o.post.flags;
     const bool done = (fl & (R6_F_EVENT | R6_F_OOB)) != 0;                    // rocket_env.py:213
     const bool trunc = !done && p.max_episode_steps > 0 && e.k >= p.max_episode_steps;   // gym TimeLimit

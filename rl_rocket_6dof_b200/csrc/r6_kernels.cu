@@ -106,7 +106,7 @@ template <class R>
 __device__ __noinline__ void stats_episode(double *stats, uint32_t flags, double ep_return, int length)
 {
     atomicAdd(&stats[R6_S_EPISODES], 1.0);
-    atomicAdd(&stats[R6_S_RETURN_SUM], ep_return);
+    if (isfinite(ep_return)) atomicAdd(&stats[R6_S_RETURN_SUM], ep_return);     // never poison the batch statistics
     atomicAdd(&stats[R6_S_LENGTH_SUM], (double)length);
     if ((flags & R6_F_LANDING_ALL) == R6_F_LANDING_ALL) atomicAdd(&stats[R6_S_LANDED], 1.0);
     if (flags & R6_F_EVENT) atomicAdd(&stats[R6_S_GROUND], 1.0);
@@ -127,6 +127,7 @@ __device__ __forceinline__ void env_load(const R6Buffers &b, int64_t n, int64_t 
     e.k = b.step_count[i];
     e.episode = b.episode_id[i];
     e.ep_return = b.ep_return[i];
+    e.tgo = b.tgo != nullptr ? b.tgo[i] : 0.0f;
 }
 template <class R>
 __device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t i, const EnvT<R> &e)
@@ -139,6 +140,7 @@ __device__ __forceinline__ void env_store(const R6Buffers &b, int64_t n, int64_t
     b.step_count[i] = e.k;
     b.episode_id[i] = e.episode;
     b.ep_return[i] = e.ep_return;
+    if (b.tgo != nullptr) b.tgo[i] = e.tgo;
 }
 
 template <class R>
@@ -230,7 +232,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         }
         if (o.finished) {
             if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
-            if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+            if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
             if (p.auto_reset) {
                 // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
@@ -360,11 +362,14 @@ integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const flo
     work_append<R>(work_view(b.work, n), n, 0, lane, i0, unfinished, i, px);
 }
 
-template <class R, bool kExact>
+// kLast = false: one attempt per env (pass 0, list 0 -> list 1); kLast = true: the remaining attempts, however many
+template <class R, bool kExact, bool kLast>
 __global__ void __launch_bounds__(kIntThreads, int_ctas<R>())
 integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__restrict__ actions, int64_t env_offset,
-                        uint64_t seed, int64_t step_index, int64_t i0, int lane, int src, int budget)
+                        uint64_t seed, int64_t step_index, int64_t i0, int lane)
 {
+    constexpr int src = kLast ? 1 : 0;
+    constexpr int budget = kLast ? (1 << 30) : 1;
     extern __shared__ double r6_smem[];
     KShared<R, kIntThreads> K;
     K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
@@ -398,7 +403,7 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
                 b.scratch[n + i] = (uint8_t)natt;
             }
         }
-        if (src == 0) work_append<R>(W, n, 1, lane, i0, unfinished, i, px);
+        if constexpr (!kLast) work_append<R>(W, n, 1, lane, i0, unfinished, i, px);
     }
 }
 
@@ -434,7 +439,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         bool reset = false;
         if (o.finished) {
             if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
-            if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+            if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
             if (p.auto_reset) {
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
                 write_terminal_state(b, n, i, e.y);
@@ -447,6 +452,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         else {                                   // the integrator already stored the state
             b.step_count[i] = e.k;
             b.ep_return[i] = e.ep_return;
+            if (b.tgo != nullptr) b.tgo[i] = e.tgo;
         }
     }
     if (b.stats) stats_steps(b.stats, i < i1 ? 1 : 0);
@@ -505,7 +511,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
                 if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
                 write_terminal_state(b, n, i, e.y);
-                if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+                if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
                 if (!p.auto_reset) {
                     // frozen: the rest of the trajectory record (if any) is padding
                     for (int jj = j + 1; jj < k_steps; jj++) {
@@ -552,7 +558,7 @@ rollout_tc_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t
     else {
 #pragma unroll
         for (int c = 0; c < 14; c++) e.y[c] = 0;
-        e.m0 = 1; e.v0 = 0; e.k = 0; e.episode = 0; e.ep_return = 0;
+        e.m0 = 1; e.v0 = 0; e.k = 0; e.episode = 0; e.ep_return = 0; e.tgo = 0;
     }
     StepOut o;
     o.reward = 0; o.flags = 0; o.finished = false; o.natt = 0; o.status = 0;
@@ -577,7 +583,7 @@ rollout_tc_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t
                 if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
                 write_obs(b.terminal_obs, n, i, p, dv, e.y);
                 write_terminal_state(b, n, i, e.y);
-                if (b.ep_info) { b.ep_info[i] = (float)e.ep_return; b.ep_info[n + i] = (float)e.k; }
+                if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
                 if (!p.auto_reset) {
                     for (int jj = j + 1; jj < k_steps; jj++) {
                         if (traj_rew) traj_rew[(int64_t)jj * n + i] = 0.0f;
@@ -626,10 +632,10 @@ sim_raw_kernel(double *state, const double *u, const double *m0, const double *t
 }
 
 __global__ void __launch_bounds__(kThreads)
-tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *out)
+tgo_kernel(const double *c2, const double *c3, const double *c4, double c0, int64_t n, const double *guess, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i]);
+    if (i < n) out[i] = tgo_largest_root(c0, c2[i], c3[i], c4[i], guess != nullptr ? guess[i] : 0.0);
 }
 
 // What a policy launch writes besides the env actions, and how the action is chosen (r6_policy_ex)
@@ -827,8 +833,10 @@ int enable_all()
     rc |= enable_smem(integrate_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
     rc |= enable_smem(integrate_first_kernel<R, false>, smem_bytes<R>() * kIntThreads / kThreads);
     rc |= enable_smem(integrate_first_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
-    rc |= enable_smem(integrate_resume_kernel<R, false>, smem_bytes<R>() * kIntThreads / kThreads);
-    rc |= enable_smem(integrate_resume_kernel<R, true>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, false, false>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, true, false>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, false, true>, smem_bytes<R>() * kIntThreads / kThreads);
+    rc |= enable_smem(integrate_resume_kernel<R, true, true>, smem_bytes<R>() * kIntThreads / kThreads);
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, false>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_PHILOX, true>, smem_bytes<R>());
     rc |= enable_smem(rollout_kernel<R, R6_ACT_BUFFER, false>, smem_bytes<R>());
@@ -885,19 +893,23 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
         if (count < 0) count = n;
         const int64_t last = first + count;
         const unsigned gi = (unsigned)((count + kIntThreads - 1) / kIntThreads);
+#ifdef R6_FAKE_STAGES
+        constexpr int smem_i = R6_FAKE_STAGES * r6::kNK * kIntThreads * (int)sizeof(R);
+#else
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
+#endif
         const bool series = p->dt <= kMaxDtSeries;
         if (b->work != nullptr) {                // integrator cut at attempt boundaries (see integrate_first_kernel)
             // list 0 holds ~2/3 of the range, list 1 ~1 %; the resume kernels walk longer lists with a grid stride
             const unsigned g1 = gi - gi / 4, g2 = gi / 16 + 1;
             if (series) {
                 integrate_first_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
-                integrate_resume_kernel<R, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 0, 1);
-                integrate_resume_kernel<R, false><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 1, 1 << 30);
+                integrate_resume_kernel<R, false, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                integrate_resume_kernel<R, false, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
             } else {
                 integrate_first_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
-                integrate_resume_kernel<R, true><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 0, 1);
-                integrate_resume_kernel<R, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane, 1, 1 << 30);
+                integrate_resume_kernel<R, true, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                integrate_resume_kernel<R, true, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
             }
         } else if (series)
             integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
@@ -1046,11 +1058,12 @@ int r6_sim_step_raw(double *state, const double *u, const double *m0, const doub
     return check_launch("r6_sim_step_raw");
 }
 
-int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, double *tgo, void *stream)
+int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int64_t n, const double *guess, double *tgo,
+           void *stream)
 {
     if (!c2 || !c3 || !c4 || !tgo) return fail(R6_EINVAL, "null pointer%s");
     if (n <= 0) return n == 0 ? R6_OK : fail(R6_EINVAL, "n < 0%s");
-    tgo_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(c2, c3, c4, c0, n, tgo);
+    tgo_kernel<<<(unsigned)blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(c2, c3, c4, c0, n, guess, tgo);
     return check_launch("r6_tgo");
 }
 

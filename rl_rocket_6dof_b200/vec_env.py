@@ -70,7 +70,6 @@ class Rocket6DOFVecEnv:
         self._flags_h = torch.empty(n, dtype=torch.uint8).pin_memory()
         self._actions = None
         self._act_in_flight = None
-        self._empty_infos: List[dict] = [{} for _ in range(n)]
         self._t_start = time.time()
         self.zero_copy = bool(zero_copy)
         if self.zero_copy:
@@ -162,9 +161,9 @@ class Rocket6DOFVecEnv:
         # [N, obs_dim] contiguous: torch's blocked transpose-copy of the pinned [obs_dim, N] buffer is several times
         # faster than numpy's strided copy
         obs = obs.copy() if obs.flags["C_CONTIGUOUS"] else self._obs_h.t().contiguous().numpy()
-        # info dicts are only materialised for envs that finished; the others get a per-env empty dict that is
-        # created once and handed out again every step (the protocol does not ask for fresh objects)
-        infos: List[dict] = list(self._empty_infos)
+        # info dicts are only filled in for envs that finished; every other env gets a FRESH empty dict each step, so a
+        # wrapper or callback that writes into infos[i] cannot leak keys into later steps
+        infos: List[dict] = [{} for _ in range(self.num_envs)]
         idx = np.nonzero(dones)[0]
         if len(idx):
             b = self.batch
@@ -180,7 +179,7 @@ class Rocket6DOFVecEnv:
                 d = dict(tpl)
                 d["landing_conditions"] = dict(tpl["landing_conditions"])
                 d["terminal_observation"] = tobs[j]
-                d["episode"] = {"r": ret[j], "l": length[j], "t": now}
+                d["episode"] = {"r": round(ret[j], 6), "l": length[j], "t": now}      # Monitor: float64 sum, 6 decimals
                 d["state_history"] = [tstate[j]]
                 infos[i] = d
         return obs, rews.copy(), dones.copy(), infos

@@ -14,7 +14,7 @@ DEPS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(ROOT, "rl_rocket_6dof_b2
 
 class HsEnv(C.Structure):
     _fields_ = [("y", C.c_double * 14), ("m0", C.c_float), ("v0", C.c_float), ("k", C.c_int32),
-                ("episode", C.c_uint32), ("ep_return", C.c_double)]
+                ("episode", C.c_uint32), ("ep_return", C.c_double), ("tgo", C.c_float), ("pad", C.c_float)]
 
 
 class HsOut(C.Structure):
@@ -39,6 +39,8 @@ def lib():
         assert L.hs_sizeof_env() == C.sizeof(HsEnv) and L.hs_sizeof_out() == C.sizeof(HsOut)
         L.hs_tgo.restype = C.c_double
         L.hs_tgo.argtypes = [C.c_double] * 4
+        L.hs_tgo_warm.restype = C.c_double
+        L.hs_tgo_warm.argtypes = [C.c_double] * 5
         L.hs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
         L.hs_sim_step_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
@@ -70,6 +72,7 @@ class HostSimBatch:
         self.envs["m0"][idx] = m0
         self.envs["k"][idx] = k
         self.envs["v0"][idx] = v0
+        self.envs["tgo"][idx] = 0.0          # a new episode starts cold
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, np.float32).reshape(self.n, 3)

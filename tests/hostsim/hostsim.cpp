@@ -18,6 +18,7 @@ struct HsEnv {
     int32_t k;
     uint32_t episode;
     double ep_return;
+    float tgo, pad;      // warm start of the t_go iteration, carried from step to step like R6Buffers.tgo
 };
 struct HsOut {
     double state[14];
@@ -39,11 +40,12 @@ void hs_step(const R6Params *p, const double *t_table, HsEnv *envs, int64_t n, c
         memcpy(e.y, envs[i].y, sizeof e.y);
         e.m0 = envs[i].m0; e.v0 = envs[i].v0; e.k = envs[i].k; e.episode = envs[i].episode;
         e.ep_return = envs[i].ep_return;
+        e.tgo = envs[i].tgo;
         StepOut o;
         if (p->dt <= kMaxDtSeries) env_step<false>(*p, dv, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o, K);
         else env_step<true>(*p, dv, t_table, e, actions[3 * i], actions[3 * i + 1], actions[3 * i + 2], o, K);
         memcpy(envs[i].y, e.y, sizeof e.y);
-        envs[i].k = e.k; envs[i].ep_return = e.ep_return;
+        envs[i].k = e.k; envs[i].ep_return = e.ep_return; envs[i].tgo = e.tgo;
         HsOut &r = outs[i];
         memcpy(r.state, e.y, sizeof e.y);
         for (int c = 0; c < 14; c++) r.obs[c] = obs_component(*p, dv, e.y, c);
@@ -62,7 +64,7 @@ void hs_reset(const R6Params *p, const R6Buffers *b, HsEnv *envs, int64_t n, int
         env_reset(*p, *b, seed, env_offset + i, e);
         memcpy(envs[i].y, e.y, sizeof e.y);
         envs[i].m0 = e.m0; envs[i].v0 = e.v0; envs[i].k = e.k; envs[i].episode = e.episode;
-        envs[i].ep_return = e.ep_return;
+        envs[i].ep_return = e.ep_return; envs[i].tgo = e.tgo;
     }
 }
 
@@ -88,8 +90,8 @@ int hs_sim_step_raw_passes(double *y, const double *u, double m0, double t, doub
         StepConst c;
         consts_raw_mode(c, m0, u[0], u[1], u[2], y[10]);
         KLocal K;
-        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 1>(c, y, t, dt, *natt, K, &px)
-                                  : integrate<true, KLocal, double, 1>(c, y, t, dt, *natt, K, &px);
+        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 1>(c, y, t, dt, *natt, K, px)
+                                  : integrate<true, KLocal, double, 1>(c, y, t, dt, *natt, K, px);
     }
     *passes = 1;
     while (st == -2) {
@@ -98,8 +100,8 @@ int hs_sim_step_raw_passes(double *y, const double *u, double m0, double t, doub
         KLocal K;
         memset(&K, 0, sizeof K);
         px.budget = 1;
-        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 2>(c, y, t, dt, *natt, K, &px)
-                                  : integrate<true, KLocal, double, 2>(c, y, t, dt, *natt, K, &px);
+        st = (dt <= kMaxDtSeries) ? integrate<false, KLocal, double, 2>(c, y, t, dt, *natt, K, px)
+                                  : integrate<true, KLocal, double, 2>(c, y, t, dt, *natt, K, px);
         (*passes)++;
     }
     normalize_quat(y);
@@ -107,6 +109,7 @@ int hs_sim_step_raw_passes(double *y, const double *u, double m0, double t, doub
 }
 
 double hs_tgo(double c0, double c2, double c3, double c4) { return tgo_largest_root(c0, c2, c3, c4); }
+double hs_tgo_warm(double c0, double c2, double c3, double c4, double guess) { return tgo_largest_root(c0, c2, c3, c4, guess); }
 
 void hs_euler_tests(const double viol[3], const double land[3], const double q[4], int *violated, int *land_ok)
 {

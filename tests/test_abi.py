@@ -44,7 +44,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     L = _lib.load()
     assert L.r6_step(None, None, 4, 0, None, 0, None) == -1
     assert b"null" in L.r6_last_error()
-    assert L.r6_tgo(None, None, None, 1.0, 4, None, None) == -1
+    assert L.r6_tgo(None, None, None, 1.0, 4, None, None, None) == -1
     assert L.r6_stats_reset(None, None) == -1
 
 

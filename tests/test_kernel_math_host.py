@@ -165,6 +165,11 @@ def test_host_tgo_vs_np_roots():
         t = L.hs_tgo(*[c[0], c[2], c[3], c[4]])
         assert abs(t - pos[0]) <= 2e-13 * pos[0], (c, t, pos)
         assert pos[0] == max(pos)
+        # warm starts: near the root, on either side, near a SMALLER positive root, useless — always the largest root
+        for g in (pos[0] * 1.01, pos[0] * 0.99, pos[0] * 1.5, pos[0] * 0.6, min(pos) * 1.001, min(pos) * 0.999,
+                  pos[0] * 1e-4, pos[0] * 1e4):
+            tw = L.hs_tgo_warm(c[0], c[2], c[3], c[4], g)
+            assert abs(tw - pos[0]) <= 2e-13 * pos[0], (c, g, tw, pos)
     assert n3 > 20
 
 
