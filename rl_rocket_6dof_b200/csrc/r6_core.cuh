@@ -539,13 +539,8 @@ using KLocal = KLocalT<double>;
 template <class R, int kThreadsPerBlock>
 struct KShared {
     R *base;   // smem + threadIdx.x
-#ifdef R6_FAKE_STAGES     /* TIMING EXPERIMENT ONLY (wrong results): fewer stage slots => more resident CTAs */
-    __device__ __forceinline__ R get(int j, int c) const { return base[((j < R6_FAKE_STAGES ? j : R6_FAKE_STAGES - 1) * kNK + c) * kThreadsPerBlock]; }
-    __device__ __forceinline__ void set(int j, int c, R v) { base[((j < R6_FAKE_STAGES ? j : R6_FAKE_STAGES - 1) * kNK + c) * kThreadsPerBlock] = v; }
-#else
     __device__ __forceinline__ R get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
     __device__ __forceinline__ void set(int j, int c, R v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
-#endif
 };
 #endif
 template <class KS, class R>
@@ -756,7 +751,7 @@ struct PassCtx {
     bool rejected;
 };
 #ifndef R6_ROWS_UNROLLED
-#define R6_ROWS_UNROLLED 1      /* 1: stage_point<ROW> per row (switch); 0: one rolled loop with constant-bank indexing */
+#define R6_ROWS_UNROLLED 1      /* 1: stage_point<ROW> per row (switch) in the pass kernels; 0: the rolled loop everywhere */
 #endif
 template <bool kExact, class KS, class R, int kPass = 0>
 R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx<R> &px)
@@ -765,6 +760,11 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     constexpr R rtol = R(1e-3), atol = R(1e-6);
     constexpr R inv_sqrt14 = R(0.2672612419124244);   // 1/sqrt(14)
     constexpr int kStageF0 = -1, kStageProbe = 0;        // stage >= 1: Dormand-Prince stage index (6 = f(y_new))
+    // The pass kernels (one RK attempt per launch, nothing else in the kernel) take the unrolled per-row stage sums:
+    // -11 % instructions, all stage loads in flight at once.  The fused step / rollout kernels keep the rolled loop:
+    // their hot footprint (integrator + reward + reset in one kernel) is what the instruction cache bounds, and the
+    // unrolled rows (+10 KB) cost them 7 % (rollout_fused 1.73e9 -> 1.61e9 env-steps/s).  Same arithmetic either way.
+    constexpr bool kUnroll = R6_ROWS_UNROLLED != 0 && kPass != 0;
     const R t_bound = t + dt;
     const R L = fabs(t_bound - t);                       // common.py:100 (interval length as SciPy computes it)
     if constexpr (kPass == 2) density_setup(c, px.h_ref);
@@ -797,19 +797,28 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             for (int i = 0; i < kNK; i++) es[i] = 0;
 #pragma unroll
             for (int i = 0; i < 3; i++) er[i] = 0;
-#if R6_ROWS_UNROLLED
+            if constexpr (kUnroll) {
 #pragma unroll
-#else
+                for (int j = 0; j < 6; j++) {
+                    const R e = T.E[j], ea = T.EA[j];
+#pragma unroll
+                    for (int i = 0; i < kNK; i++) {
+                        if (j == 1 && i >= 3) continue;                       // E[1] = 0: only EA[1] K_1[0..2] counts
+                        const R k = K.get(j, i);
+                        if (j != 1) es[i] = fma(e, k, es[i]);
+                        if (i < 3) er[i] = fma(ea, k, er[i]);
+                    }
+                }
+            } else {
 #pragma unroll 1
-#endif
-            for (int j = 0; j < 6; j++) {
-                const R e = T.E[j], ea = T.EA[j];
+                for (int j = 0; j < 6; j++) {
+                    const R e = T.E[j], ea = T.EA[j];
 #pragma unroll
-                for (int i = 0; i < kNK; i++) {
-                    if (R6_ROWS_UNROLLED && j == 1 && i >= 3) continue;       // E[1] = 0: only EA[1] K_1[0..2] counts
-                    const R k = K.get(j, i);
-                    if (!(R6_ROWS_UNROLLED && j == 1)) es[i] = fma(e, k, es[i]);
-                    if (i < 3) er[i] = fma(ea, k, er[i]);
+                    for (int i = 0; i < kNK; i++) {
+                        const R k = K.get(j, i);
+                        es[i] = fma(e, k, es[i]);
+                        if (i < 3) er[i] = fma(ea, k, er[i]);
+                    }
                 }
             }
             const R e6 = T.E[6];
@@ -920,18 +929,17 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             row = 1; hh = h;
         }
         // ---- evaluation point of the next RHS call: rk_step (rk.py:58-66) with the row's coefficients ----
-#if R6_ROWS_UNROLLED
-        switch (row) {
-        case 1: stage_point<1>(K, y, hh, c.dm, x); break;
-        case 2: stage_point<2>(K, y, hh, c.dm, x); break;
-        case 3: stage_point<3>(K, y, hh, c.dm, x); break;
-        case 4: stage_point<4>(K, y, hh, c.dm, x); break;
-        case 5: stage_point<5>(K, y, hh, c.dm, x); break;
-        case 6: stage_point<6>(K, y, hh, c.dm, x); break;
-        default: stage_point<7>(K, y, hh, c.dm, x); break;
-        }
-#else
-        {
+        if constexpr (kUnroll) {
+            switch (row) {
+            case 1: stage_point<1>(K, y, hh, c.dm, x); break;
+            case 2: stage_point<2>(K, y, hh, c.dm, x); break;
+            case 3: stage_point<3>(K, y, hh, c.dm, x); break;
+            case 4: stage_point<4>(K, y, hh, c.dm, x); break;
+            case 5: stage_point<5>(K, y, hh, c.dm, x); break;
+            case 6: stage_point<6>(K, y, hh, c.dm, x); break;
+            default: stage_point<7>(K, y, hh, c.dm, x); break;
+            }
+        } else {
             R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
 #pragma unroll
             for (int i = 0; i < kNK; i++) acc[i] = 0;
@@ -954,7 +962,6 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
             x.w1 = fma(hh, acc[7], y[11]); x.w2 = fma(hh, acc[8], y[12]);
             x.m = fma(hc, c.dm, y[13]);
         }
-#endif
     }
     return status;
 }
@@ -989,55 +996,11 @@ R6_HD W quartic_df(W c0, W c2, W c3, W t)
 {
     return fma(fma(4 * c0, t * t, 2 * c2), t, c3);
 }
-// `guess` (optional warm start, 0 = none): the root found for the same env one step earlier.  t_go moves by about dt
-// per env-step, so Newton from the previous root needs 3-4 steps instead of the ~10 + 3 of the cold start from the
-// Fujiwara bound.  A warm result is accepted only when it is CERTIFIED to be the largest positive root:
-//   (A) f(t_i) <= 0 (or no inflection point): the largest root is the only root right of t_i, where f is convex and
-//       tends to +inf — any converged iterate x > t_i with f'(x) > 0 is it;
-//   (B) f(t_i) > 0 and f'(t_i) >= 0: f' has its minimum at t_i, so f increases on all of t > 0 and has exactly one
-//       positive root, inside (0, t_i) — any converged iterate there is it.
-// Anything else — the third sign pattern (a local minimum right of t_i decides), an iterate leaving the interval, a
-// non-positive slope, no convergence in 6 steps — falls back to the cold start below.
+// Cold start of tgo_largest_root (no usable warm start): bracketing by the convexity analysis above + safeguarded Newton.
+// Out of line: with R6Buffers.tgo the step kernels take it for freshly reset envs and the rare third sign pattern only.
 template <class W>
-R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4, W guess = W(0))
+R6_HD_NOINLINE W tgo_cold_start(W c0, W c2, W c3, W c4, W ic0, W ti)
 {
-    if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return W(NAN);       // no sign change => no positive root
-    const W ic0 = fast_rcp(c0);
-    const W ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * W(1.0 / 6)) : W(0.0);
-    if (guess > 0) {
-        W lo = ti, hi = W(INFINITY);                              // case (A)
-        bool usable = true;
-        if (ti > 0) {
-            const W fi = quartic_f(c0, c2, c3, c4, ti);
-            if (fi > 0) {
-                if (quartic_df(c0, c2, c3, ti) >= 0) { lo = 0; hi = ti; }      // case (B)
-                else usable = false;
-            }
-        }
-        W x = fmin(guess, hi);
-        if (usable && x > lo) {
-            W fx = quartic_f(c0, c2, c3, c4, x), dx = x;
-            bool conv = false;
-#pragma unroll 1
-            for (int it = 0; it < 6; it++) {
-                const W dfx = quartic_df(c0, c2, c3, x);
-                if (!(dfx > 0)) break;
-                dx = fx * fast_rcp(dfx);
-                x -= dx;
-                if (!(x > lo && x <= hi)) break;
-                fx = quartic_f(c0, c2, c3, c4, x);
-                // quadratic convergence: a correction below 1e-8 x leaves an error of ~1e-16 x
-                if (fabs(dx) <= W(sizeof(W) == 8 ? 1e-8 : 1e-4) * x) { conv = true; break; }
-            }
-            if (conv) {
-                const W dfx = quartic_df(c0, c2, c3, x);
-                if (dfx > 0) {
-                    const W xn = x - fx * fast_rcp(dfx);          // polish: rounding level
-                    if (xn > lo && xn <= hi) return xn;
-                }
-            }
-        }
-    }
     // Fujiwara bound on the root moduli; float32 is plenty for a bound (inflated by 1e-4)
     const float a2 = (float)(fabs(c2) * ic0), a1 = (float)(fabs(c3) * ic0), a0 = (float)(fabs(c4) * ic0);
     const W B = (W)(2.0002f * fmaxf(sqrtf(a2), fmaxf(cbrtf(a1), sqrtf(sqrtf(0.5f * a0)))));
@@ -1135,6 +1098,58 @@ R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4, W guess = W(0))
         }
     }
     return x;
+}
+
+// `guess` (optional warm start, 0 = none): the root found for the same env one step earlier.  t_go moves by about dt
+// per env-step, so Newton from the previous root needs 3-4 steps instead of the ~10 + 3 of the cold start from the
+// Fujiwara bound.  A warm result is accepted only when it is CERTIFIED to be the largest positive root:
+//   (A) f(t_i) <= 0 (or no inflection point): the largest root is the only root right of t_i, where f is convex and
+//       tends to +inf — any converged iterate x > t_i with f'(x) > 0 is it;
+//   (B) f(t_i) > 0 and f'(t_i) >= 0: f' has its minimum at t_i, so f increases on all of t > 0 and has exactly one
+//       positive root, inside (0, t_i) — any converged iterate there is it.
+// Anything else — the third sign pattern (a local minimum right of t_i decides), an iterate leaving the interval, a
+// non-positive slope, no convergence in 6 steps — falls back to the cold start below.
+template <class W>
+R6_HD W tgo_largest_root(W c0, W c2, W c3, W c4, W guess = W(0))
+{
+    if (!(c4 < 0) && !(c3 < 0) && !(c2 < 0)) return W(NAN);       // no sign change => no positive root
+    const W ic0 = fast_rcp(c0);
+    const W ti = (c2 < 0) ? fast_sqrt(-c2 * ic0 * W(1.0 / 6)) : W(0.0);
+    if (guess > 0) {
+        W lo = ti, hi = W(INFINITY);                              // case (A)
+        bool usable = true;
+        if (ti > 0) {
+            const W fi = quartic_f(c0, c2, c3, c4, ti);
+            if (fi > 0) {
+                if (quartic_df(c0, c2, c3, ti) >= 0) { lo = 0; hi = ti; }      // case (B)
+                else usable = false;
+            }
+        }
+        W x = fmin(guess, hi);
+        if (usable && x > lo) {
+            W fx = quartic_f(c0, c2, c3, c4, x), dx = x;
+            bool conv = false;
+#pragma unroll 1
+            for (int it = 0; it < 6; it++) {
+                const W dfx = quartic_df(c0, c2, c3, x);
+                if (!(dfx > 0)) break;
+                dx = fx * fast_rcp(dfx);
+                x -= dx;
+                if (!(x > lo && x <= hi)) break;
+                fx = quartic_f(c0, c2, c3, c4, x);
+                // quadratic convergence: a correction below 1e-8 x leaves an error of ~1e-16 x
+                if (fabs(dx) <= W(sizeof(W) == 8 ? 1e-8 : 1e-4) * x) { conv = true; break; }
+            }
+            if (conv) {
+                const W dfx = quartic_df(c0, c2, c3, x);
+                if (dfx > 0) {
+                    const W xn = x - fx * fast_rcp(dfx);          // polish: rounding level
+                    if (xn > lo && xn <= hi) return xn;
+                }
+            }
+        }
+    }
+    return tgo_cold_start(c0, c2, c3, c4, ic0, ti);
 }
 
 // ------------------------------------------------------------------------------------------------

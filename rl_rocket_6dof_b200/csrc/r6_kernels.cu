@@ -99,6 +99,7 @@ __device__ __forceinline__ KStore<R> make_kstore()
 // no accumulator registers carried through the step.
 __device__ __forceinline__ void stats_steps(double *stats, int my_steps)
 {
+
     const int tot = __reduce_add_sync(0xffffffffu, my_steps);
     if ((threadIdx.x & 31) == 0 && tot != 0) atomicAdd(&stats[R6_S_STEPS], (double)tot);
 }
@@ -408,7 +409,8 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
 }
 
 #ifndef R6_POST_BLOCKS
-#define R6_POST_BLOCKS 6         /* resident post-step CTAs per SM (no stage storage: registers are the only limit) */
+#define R6_POST_BLOCKS 7         /* resident post-step CTAs per SM (no stage storage: registers are the only limit);
+                                    5 (94 registers, no spills) .. 8 (64 registers) measured within 2 % of each other */
 #endif
 template <class R>
 __global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
@@ -424,8 +426,10 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         float a0, a1, a2;
         if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
         else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
+        const int status = (int)(int8_t)b.scratch[i], natt = (int)b.scratch[n + i];
+        write_obs(b.obs, n, i, p, dv, e.y);          // first thing: the float64 state is then dead but for q and the casts
         StepOut o;
-        env_post(p, dv, e, a0, a1, a2, (int)(int8_t)b.scratch[i], (int)b.scratch[n + i], o);
+        env_post(p, dv, e, a0, a1, a2, status, natt, o);
         if (b.reward) b.reward[i] = o.reward;
         if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
         b.done[i] = o.finished ? 1 : 0;
@@ -436,20 +440,24 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
 #pragma unroll
             for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
         }
-        bool reset = false;
         if (o.finished) {
+            // rare (one env-step in ~140): the post-step state is read back from `state` (nothing has written it since
+            // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake
             if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
             if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
             if (p.auto_reset) {
-                write_obs(b.terminal_obs, n, i, p, dv, e.y);
-                write_terminal_state(b, n, i, e.y);
+                const R *state = reinterpret_cast<const R *>(b.state);
+                R yt[14];
+#pragma unroll
+                for (int c = 0; c < 14; c++) yt[c] = state[(int64_t)c * n + i];
+                write_obs(b.terminal_obs, n, i, p, dv, yt);
+                write_terminal_state(b, n, i, yt);
                 env_reset(p, b, seed, env_offset + i, e);
-                reset = true;
+                write_obs(b.obs, n, i, p, dv, e.y);          // replaces the terminal observation written above
+                env_store(b, n, i, e);
             }
         }
-        write_obs(b.obs, n, i, p, dv, e.y);
-        if (reset) env_store(b, n, i, e);
-        else {                                   // the integrator already stored the state
+        if (!(o.finished && p.auto_reset)) {         // the integrator already stored the state
             b.step_count[i] = e.k;
             b.ep_return[i] = e.ep_return;
             if (b.tgo != nullptr) b.tgo[i] = e.tgo;
@@ -893,11 +901,7 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
         if (count < 0) count = n;
         const int64_t last = first + count;
         const unsigned gi = (unsigned)((count + kIntThreads - 1) / kIntThreads);
-#ifdef R6_FAKE_STAGES
-        constexpr int smem_i = R6_FAKE_STAGES * r6::kNK * kIntThreads * (int)sizeof(R);
-#else
         constexpr int smem_i = smem_bytes<R>() * kIntThreads / kThreads;
-#endif
         const bool series = p->dt <= kMaxDtSeries;
         if (b->work != nullptr) {                // integrator cut at attempt boundaries (see integrate_first_kernel)
             // list 0 holds ~2/3 of the range, list 1 ~1 %; the resume kernels walk longer lists with a grid stride
