@@ -68,3 +68,16 @@ def test_params_match_reference_constants():
     for key, mine in (("ic_low", ep.ic_low), ("ic_high", ep.ic_high)):
         if key in g.files:
             assert np.array_equal(mine, g[key])
+
+
+def test_build_is_keyed_on_a_source_hash(tmp_path, monkeypatch):
+    """build() decides staleness by a hash of csrc/*.cu*, include/*.h and the flags (not by mtimes), and its
+    dependency list covers every header the library includes."""
+    from rl_rocket_6dof_b200 import build as b
+    names = {os.path.basename(d) for d in b.deps()}
+    assert {"r6_kernels.cu", "r6_core.cuh", "r6_mlp_tc.cuh", "r6_mlp_tcgen05.cuh", "r6dof.h"} <= names
+    b.build()
+    assert not b.needs_build() and b.built_hash() == b.source_hash()
+    h0 = b.source_hash()
+    monkeypatch.setattr(b, "NVCC_FLAGS", b.NVCC_FLAGS + ["-DSOMETHING"])
+    assert b.source_hash() != h0 and b.needs_build()
