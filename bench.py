@@ -377,7 +377,8 @@ def run_b200(args):
     # closed loop as two kernels per env-step (r6_policy + r6_step): what a VecEnv consumer with the policy on
     # the device runs; 2 launches per step
     ms_two = {}
-    for tc in (0, 1, 2):
+    ms_pol_kernel = {}
+    for tc in (0, 1, 2, 3):
         env.step_policy(W, wdev, tensor_cores=tc)
         barrier()
         e0.record(stream)
@@ -385,6 +386,13 @@ def run_b200(args):
         e1.record(stream)
         torch.cuda.synchronize()
         ms_two[tc] = max_over_ranks(e0.elapsed_time(e1))
+        barrier()
+        e0.record(stream)
+        for _ in range(K):
+            env.policy_actions(wdev, tensor_cores=tc, out=env._policy_act)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_pol_kernel[tc] = max_over_ranks(e0.elapsed_time(e1)) / K
         barrier()
 
     # PPO rollout collection on the device: stochastic Gaussian policy (tcgen05 mode) + value head + env step per
@@ -396,10 +404,10 @@ def run_b200(args):
                    log_std=np.array([-1.44, -2.07, -2.01], np.float32))
     wacd = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in wac.items()}
     KC = max(min(K, 32), 1)
-    env.collect_rollout(KC, wacd, tensor_cores=2)          # also warms the allocator for the [KC, N, ...] buffers
+    env.collect_rollout(KC, wacd, tensor_cores=3)          # also warms the allocator for the [KC, N, ...] buffers
     barrier()
     e0.record(stream)
-    env.collect_rollout(KC, wacd, tensor_cores=2)
+    env.collect_rollout(KC, wacd, tensor_cores=3)
     e1.record(stream)
     torch.cuda.synchronize()
     ms_collect = max_over_ranks(e0.elapsed_time(e1))
@@ -539,8 +547,16 @@ def run_b200(args):
                                             "ms_per_step": ms_two[2] / K, "launches_per_step": 2,
                                             "actions": "r6_policy (tcgen05.mma kind::tf32, TMEM accumulators, single-pass TF32: "
                                                        "|d action| ~1e-3) then r6_step"},
+        "closed_loop_two_kernels_tcgen05_3xtf32": {"value": world * n * K / (ms_two[3] * 1e-3), "unit": UNIT,
+                                                   "ms_per_step": ms_two[3] / K, "launches_per_step": 2,
+                                                   "actions": "r6_policy (tcgen05.mma kind::tf32, 3xTF32 compensation in one TMEM "
+                                                              "accumulator, float32-accurate tanh: |d action| <= 3e-6 vs the "
+                                                              "reference's recorded actions) then r6_step — the faithful "
+                                                              "closed loop on the 5th-generation tensor cores"},
+        "policy_kernel_ms": {"fp32_fma": ms_pol_kernel[0], "mma_sync_3xtf32": ms_pol_kernel[1], "tcgen05_tf32": ms_pol_kernel[2],
+                             "tcgen05_3xtf32": ms_pol_kernel[3], "envs": n},
         "ppo_collect_rollout": {"value": world * n * KC / (ms_collect * 1e-3), "unit": UNIT, "ms_per_step": ms_collect / KC,
-                                "steps": KC, "what": "stochastic Gaussian policy + value head (r6_policy_ex, tcgen05 mode), r6_step, "
+                                "steps": KC, "what": "stochastic Gaussian policy + value head (r6_policy_ex, faithful tcgen05 3xTF32 mode), r6_step, "
                                                      "[T,N] buffers written on the device, then the GAE scan (r6_gae)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K,

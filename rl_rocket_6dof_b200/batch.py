@@ -282,7 +282,7 @@ class Rocket6DOFBatch:
     def policy_actions(self, mlp: dict, *, tensor_cores=False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Deterministic policy actions [N, 3] for the current observations (one r6_policy launch).
         tensor_cores: False / 0 = float32 FMA network; True / 1 = mma.sync 3xTF32 tiles (faithful to 2e-6);
-        2 = tcgen05 + TMEM single-pass TF32 (fast mode, ~1e-3)."""
+        2 = tcgen05 + TMEM single-pass TF32 (fast mode, ~1e-3); 3 = tcgen05 + TMEM 3xTF32 (faithful to 3e-6)."""
         self.join()
         if out is None:
             out = torch.empty(self.num_envs, 3, dtype=torch.float32, device=self.device)
@@ -316,10 +316,10 @@ class Rocket6DOFBatch:
         return act, raw, val, logp
 
     def collect_rollout(self, k: int, mlp: dict, *, gamma: float = 0.99, gae_lambda: float = 0.95,
-                        stochastic: bool = True, tensor_cores=False) -> dict:
+                        stochastic: bool = True, tensor_cores=3) -> dict:
         """What SB3's `PPO.collect_rollouts` + `RolloutBuffer.compute_returns_and_advantage` produce for k steps of
-        this VecEnv, entirely on the device: per step one policy launch (action, value, log-prob), one env step; then
-        the GAE scan.  Returns tensors shaped [k, N, ...]: obs (13), actions (raw Gaussian samples), values, log_probs,
+        this VecEnv, entirely on the device: per step one policy launch (action, value, log-prob; by default the
+        faithful tcgen05 3xTF32 kernel, tensor_cores=3), one env step; then the GAE scan.  Returns tensors shaped [k, N, ...]: obs (13), actions (raw Gaussian samples), values, log_probs,
         rewards, dones, advantages, returns.  (Bootstrapping time-limit truncations with the critic is left to the
         caller, as in `gae.compute_gae`.)"""
         from .gae import compute_gae
@@ -366,7 +366,7 @@ class Rocket6DOFBatch:
         return dict(obs=obs, actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones, advantages=adv,
                     returns=ret, last_values=last_v)
 
-    def step_policy(self, k: int, mlp: dict, *, tensor_cores=False, join: bool = True):
+    def step_policy(self, k: int, mlp: dict, *, tensor_cores=3, join: bool = True):
         """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes
         the actions, the step kernel consumes them — VecEnv semantics (auto-reset as configured).  Faster than the
         single fused rollout kernel for large batches; `rollout(k, ACT_MLP)` remains for one-episode semantics.

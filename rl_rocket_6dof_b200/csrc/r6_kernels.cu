@@ -783,6 +783,112 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, con
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
 }
 
+// The policy on tcgen05 / TMEM at float32 accuracy (r6_policy tensor_cores = 3): 3xTF32-compensated operands, two
+// 128-env tile groups per CTA over one resident copy of the split weights — see r6_mlp_tcgen05.cuh (namespace tc5x3).
+__global__ void __launch_bounds__(tc5x3::kThreads, 1)
+policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
+{
+    using namespace tc5x3;
+    extern __shared__ double r6_smem[];
+    char *S = reinterpret_cast<char *>(r6_smem);
+    const int tid = threadIdx.x, group = tid >> 7, lt = tid & 127, warp = tid >> 5;
+    // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
+    for (int idx = tid; idx < 128 * 16; idx += kThreads) {
+        const int r = idx >> 4, k = idx & 15;
+        float hi, lo;
+        split_tf32(k < kMlpIn ? mlp.w0[r * kMlpIn + k] : 0.0f, hi, lo);
+        *reinterpret_cast<float *>(S + kOffW0h + tile_off(r, k, 16)) = hi;
+        *reinterpret_cast<float *>(S + kOffW0l + tile_off(r, k, 16)) = lo;
+    }
+    for (int idx = tid; idx < 64 * 128; idx += kThreads) {
+        const int r = idx >> 7, k = idx & 127;
+        float hi, lo;
+        split_tf32(mlp.w1[r * kMlpH0 + k], hi, lo);
+        *reinterpret_cast<float *>(S + kOffW1h + tile_off(r, k, 128)) = hi;
+        *reinterpret_cast<float *>(S + kOffW1l + tile_off(r, k, 128)) = lo;
+    }
+    for (int idx = tid; idx < 16 * 64; idx += kThreads) {
+        const int r = idx >> 6, k = idx & 63;
+        float hi, lo;
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, hi, lo);
+        *reinterpret_cast<float *>(S + kOffW2h + tile_off(r, k, 64)) = hi;
+        *reinterpret_cast<float *>(S + kOffW2l + tile_off(r, k, 64)) = lo;
+    }
+    float *bias = reinterpret_cast<float *>(S + kOffBias3);
+    if (tid < 128) bias[tid] = mlp.b0[tid];
+    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
+    if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar3)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar3 + 8)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtr3)), "n"(kTmemCols3) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtr3);
+    const uint32_t tmem_g = tmem_base + (uint32_t)group * kGroupCols;                      // this group's columns, lane 0
+    const uint32_t tmem_row = tmem_g + ((uint32_t)((warp & 3) * 32) << 16);                // this warp's 32 TMEM lanes
+    char *Hh = S + kOffGroup + group * kGroupBytes, *Hl = Hh + kOffHl;                     // the input tile aliases their heads
+    const uint32_t aHh = smem_u32(Hh), aHl = smem_u32(Hl);
+    const uint32_t aW0h = smem_u32(S + kOffW0h), aW0l = smem_u32(S + kOffW0l), aW1h = smem_u32(S + kOffW1h);
+    const uint32_t aW1l = smem_u32(S + kOffW1l), aW2h = smem_u32(S + kOffW2h), aW2l = smem_u32(S + kOffW2l);
+    const uint32_t bar = smem_u32(S + kOffBar3 + 8 * group);
+    uint32_t phase = 0;
+    const int64_t i1 = po.i1;
+    const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
+    for (int64_t tile = 2 * (int64_t)blockIdx.x + group; tile < tiles; tile += 2 * (int64_t)gridDim.x) {
+        const int64_t i = po.i0 + tile * kTile + lt;
+        // ---- observations of this thread's env, split -> row `lt` of the input tiles ----
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++) {
+            float4 h, l;
+            split_tf32((4 * kc + 0 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 0) * n + i] : 0.0f, h.x, l.x);
+            split_tf32((4 * kc + 1 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 1) * n + i] : 0.0f, h.y, l.y);
+            split_tf32((4 * kc + 2 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 2) * n + i] : 0.0f, h.z, l.z);
+            split_tf32((4 * kc + 3 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 3) * n + i] : 0.0f, h.w, l.w);
+            *reinterpret_cast<float4 *>(Hh + tile_off(lt, 4 * kc, 16)) = h;
+            *reinterpret_cast<float4 *>(Hl + tile_off(lt, 4 * kc, 16)) = l;
+        }
+        fence_async_smem(); fence_before(); group_sync(group);
+        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD0, aHh, aHl, 512, aW0h, aW0l, 512, 2, 128, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
+        epilogue_to_h3(tmem_row, kColD0, bias, Hh, Hl, lt);
+        fence_async_smem(); fence_before(); group_sync(group);
+        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h, aW1l, 4096, 8, 64, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- second half ----
+        epilogue_to_h3(tmem_row, kColD0 + 64, bias + 64, Hh, Hl, lt);
+        fence_async_smem(); fence_before(); group_sync(group);
+        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 1 -> output layer ----
+        epilogue_to_h3(tmem_row, kColD1, bias + 128, Hh, Hl, lt);
+        fence_async_smem(); fence_before(); group_sync(group);
+        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD2, aHh, aHl, 2048, aW2h, aW2l, 2048, 8, 16, false); mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        {
+            float v[32];
+            tmem_ld32(tmem_row + kColD2, v);
+            if (i < i1) {
+                const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
+                policy_epilogue(po, mlp.log_std, i, out);
+            }
+        }
+        fence_before(); group_sync(group);       // every warp of the group has read D2 before the next tile's MMAs overwrite D0..D2
+        fence_after();
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols3) : "memory");
+}
+
 // GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
 // envs).  HBM-bound: 17 B per (t, env).  No FMA contraction: the float32 roundings are NumPy's.
 __global__ void __launch_bounds__(256)
@@ -864,6 +970,7 @@ int ensure_attributes()
     rc |= enable_smem(policy_kernel<true>, kSmemPolicyTc);
     rc |= enable_smem(policy_kernel<false>, kSmemPolicy);
     rc |= enable_smem(policy_tc5_kernel, tc5::kSmemBytes);
+    rc |= enable_smem(policy_tc5x3_kernel, tc5x3::kSmemBytes3);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -1080,7 +1187,7 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
     if (!obs || !actions) return fail(R6_EINVAL, "null pointer%s");
     if (n < 0) return fail(R6_EINVAL, "n < 0%s");
     if (first < 0 || count < 0 || first + count > n) return fail(R6_EINVAL, "env sub-range outside [0, n)%s");
-    if (tensor_cores < 0 || tensor_cores > 2) return fail(R6_EINVAL, "tensor_cores must be 0, 1 or 2%s");
+    if (tensor_cores < 0 || tensor_cores > 3) return fail(R6_EINVAL, "tensor_cores must be 0, 1, 2 or 3%s");
     if (count == 0) return R6_OK;
     int rc = ensure_attributes();
     if (rc) return rc;
@@ -1094,7 +1201,11 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
     const PolicyOut po = {actions, actions_raw, values, log_prob, stochastic, seed, env_offset, step_index, first, first + count};
     const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
     const unsigned g = (unsigned)(blocks_for(count) < wave ? blocks_for(count) : wave);
-    if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+    if (tensor_cores == 3) {
+        const int64_t pairs = (blocks_for(count) + 1) / 2;                 // one CTA per SM, two tile groups per CTA
+        const unsigned g3 = (unsigned)(pairs < sm_count ? pairs : sm_count);
+        policy_tc5x3_kernel<<<g3, tc5x3::kThreads, tc5x3::kSmemBytes3, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+    } else if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     return check_launch("r6_policy");

@@ -141,4 +141,81 @@ __device__ __forceinline__ void issue_mmas(uint32_t d_tmem, uint32_t a_base, uin
 }
 
 }  // namespace tc5
+
+// ------------------------------------------------------------------------------------------------------------------
+// The FAITHFUL policy mode on the 5th-generation tensor cores (r6_policy tensor_cores = 3): 3xTF32 error compensation
+// — every operand split x = hi + lo, hi = round_tf32(x), lo = round_tf32(x - hi), and hi*hi + lo*hi + hi*lo chained
+// into ONE TMEM accumulator (three tcgen05.mma per K-block, the dropped lo*lo term is 2^-22 relative) — with an
+// float32-accurate tanh, so the actions agree with the float32 FMA network to ~1e-6 (tests/test_gpu_policy.py) instead
+// of the 1e-3 of the single-pass mode above.
+//
+// The split operands need twice the shared memory (weights hi + lo: 88 KB), which rules out two CTAs per SM — and one
+// CTA of four epilogue warps cannot keep the XU / FP32 pipes busy while its MMAs are in flight.  So ONE CTA per SM
+// carries TWO independent 128-env tile groups (warps 0-3 and 4-7) over one resident copy of the weights: each group
+// has its own activation tiles, TMEM columns, mbarrier and named barrier, its own elected MMA-issuing thread, and walks
+// its own tiles; while one group waits for its MMAs the other is in an epilogue.  The 16-wide input tile aliases the
+// first 8 KB of the group's hidden-activation tile (it is dead once layer 0 has been committed and waited for).
+//   shared memory: W0h W0l (8+8) | W1h W1l (32+32) | W2h W2l (4+4) | group 0: Hh Hl (32+32) | group 1: Hh Hl | bias
+//   = 88 + 128 KB + 1 KB;  TMEM: 512 columns, group g at column 256 g: D0 [0,128) D1 [128,192) D2 [192,208).
+namespace tc5x3 {
+using namespace tc5;
+constexpr int kThreads = 256;
+constexpr int kOffW0h = 0, kOffW0l = 8 << 10, kOffW1h = 16 << 10, kOffW1l = 48 << 10, kOffW2h = 80 << 10, kOffW2l = 84 << 10;
+constexpr int kOffGroup = 88 << 10, kGroupBytes = 64 << 10, kOffHl = 32 << 10;       // per group: Hh at +0, Hl at +32 KB
+constexpr int kOffBias3 = kOffGroup + 2 * kGroupBytes;                               // b0[128] b1[64] b2[4]
+constexpr int kOffBar3 = kOffBias3 + (128 + 64 + 4) * 4;                             // two mbarriers
+constexpr int kOffTmemPtr3 = kOffBar3 + 16;
+constexpr int kSmemBytes3 = kOffTmemPtr3 + 16;
+constexpr uint32_t kTmemCols3 = 512, kGroupCols = 256;
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo)
+{
+    hi = round_tf32(x);
+    lo = round_tf32(x - hi);
+}
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the exp2 / rcp units: absolute error ~1.5e-7 (the float32 ulp at 1 is 6e-8),
+// saturates correctly (exp -> inf => 1, exp -> 0 => -1)
+__device__ __forceinline__ float tanh_f32(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));      // exp(2x) = 2^(2x log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+
+// tanh(D[:, col0 .. col0+63] + bias) of this thread's row, split -> the group's Hh / Hl tiles [128][64]
+__device__ __forceinline__ void epilogue_to_h3(uint32_t tmem_row, uint32_t col0, const float *bias, char *Hh, char *Hl, int row)
+{
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_row + col0 + cc, v);
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+            float4 h, l;
+            split_tf32(tanh_f32(v[q] + bias[cc + q]), h.x, l.x);
+            split_tf32(tanh_f32(v[q + 1] + bias[cc + q + 1]), h.y, l.y);
+            split_tf32(tanh_f32(v[q + 2] + bias[cc + q + 2]), h.z, l.z);
+            split_tf32(tanh_f32(v[q + 3] + bias[cc + q + 3]), h.w, l.w);
+            const int off = tile_off(row, cc + q, 64);
+            *reinterpret_cast<float4 *>(Hh + off) = h;
+            *reinterpret_cast<float4 *>(Hl + off) = l;
+        }
+    }
+}
+// nk K-blocks of D (+)= (Ah + Al)(Bh + Bl)^T without the lo*lo term; hi*hi first, then the two corrections
+__device__ __forceinline__ void issue_mmas3(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t a_sbo, uint32_t bh, uint32_t bl,
+                                            uint32_t b_sbo, int nk, int n, bool accumulate_first)
+{
+    const uint32_t idesc = instr_desc(n);
+    for (int kb = 0; kb < nk; kb++) {
+        const uint64_t dah = smem_desc(ah + kb * 256, 128, a_sbo), dal = smem_desc(al + kb * 256, 128, a_sbo);
+        const uint64_t dbh = smem_desc(bh + kb * 256, 128, b_sbo), dbl = smem_desc(bl + kb * 256, 128, b_sbo);
+        mma_tf32(d_tmem, dah, dbh, idesc, accumulate_first || kb > 0);
+        mma_tf32(d_tmem, dal, dbh, idesc, true);
+        mma_tf32(d_tmem, dah, dbl, idesc, true);
+    }
+}
+}  // namespace tc5x3
 }  // namespace r6
