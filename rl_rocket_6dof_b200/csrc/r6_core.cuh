@@ -689,30 +689,48 @@ template <class R>
 struct EvalPoint {
     R h, r1, r2, v0, v1, v2, q0, q1, q2, q3, w1, w2, m;
 };
+// The row's newest stage (K_{ROW-1}, rows 2..6) has just been produced and is still in registers: it is taken from
+// `dn` instead of being read back.  Row 6 reads every stage, so it also forms the error-estimate sums
+// es = sum_j E[j] K_j, er = sum_j EA[j] K_j[0..2] (rk.py:104-109) on the same loads; only E[6] f(y_new) is added later.
+template <class R>
+struct ErrSums {
+    R es[kNK], er[3];
+};
 template <int ROW, class KS, class R>
-R6_HD void stage_point(const KS &K, const R *y, R hh, R dm, EvalPoint<R> &x)
+R6_HD void stage_point(const KS &K, const R *y, R hh, R dm, EvalPoint<R> &x, const DerivT<R> &dn, ErrSums<R> &E)
 {
     const TabT<R> &T = tab<R>();
     constexpr int cnt = ROW < 6 ? ROW : (ROW == 6 ? 6 : 1);
     constexpr bool kHoriz = ROW == 6;            // horizontal positions only for y_new
     constexpr bool kPos = ROW != 7;              // row 7 (probe) has no h^2 term
+    constexpr bool kErr = ROW == 6;
+    const R dnv[kNK] = {dn.dv0, dn.dv1, dn.dv2, dn.dq0, dn.dq1, dn.dq2, dn.dq3, dn.dw1, dn.dw2};
     R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
 #pragma unroll
     for (int j = 0; j < cnt; j++) {
-        const bool skip_a = (ROW == 6 && j == 1);
+        const bool skip_a = (ROW == 6 && j == 1);                  // B[1] = E[1] = 0
+        const bool newest = ROW >= 2 && ROW <= 6 && j == ROW - 1;
         const R a = T.SA[ROW][j], aa = T.SAA[ROW][j];
-        const R k0 = K.get(j, 0);
+        const R e = kErr ? T.E[j] : R(0), ea = kErr ? T.EA[j] : R(0);
+        R k[kNK];
+#pragma unroll
+        for (int i = 0; i < kNK; i++) {
+            const bool needed = !skip_a || (i == 0 && kPos) || (i < 3 && kHoriz);
+            k[i] = !needed ? R(0) : (newest ? dnv[i] : K.get(j, i));
+        }
         // j = 0 starts the sums with a product (no zeroed accumulators); SAA[ROW][0] = 0 only for ROW = 1 and 7
-        if (!skip_a) acc[0] = j == 0 ? a * k0 : fma(a, k0, acc[0]);
-        if (kPos) ar0 = j == 0 ? aa * k0 : fma(aa, k0, ar0);
-        if (!skip_a || kHoriz) {
-            const R k1 = K.get(j, 1), k2 = K.get(j, 2);
-            if (!skip_a) { acc[1] = j == 0 ? a * k1 : fma(a, k1, acc[1]); acc[2] = j == 0 ? a * k2 : fma(a, k2, acc[2]); }
-            if (kHoriz) { ar1 = j == 0 ? aa * k1 : fma(aa, k1, ar1); ar2 = j == 0 ? aa * k2 : fma(aa, k2, ar2); }
+        if (kPos) ar0 = j == 0 ? aa * k[0] : fma(aa, k[0], ar0);
+        if (kHoriz) { ar1 = j == 0 ? aa * k[1] : fma(aa, k[1], ar1); ar2 = j == 0 ? aa * k[2] : fma(aa, k[2], ar2); }
+        if (kErr) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) E.er[i] = j == 0 ? ea * k[i] : fma(ea, k[i], E.er[i]);
         }
         if (!skip_a) {
 #pragma unroll
-            for (int i = 3; i < kNK; i++) acc[i] = j == 0 ? a * K.get(j, i) : fma(a, K.get(j, i), acc[i]);
+            for (int i = 0; i < kNK; i++) {
+                acc[i] = j == 0 ? a * k[i] : fma(a, k[i], acc[i]);
+                if (kErr) E.es[i] = j == 0 ? e * k[i] : fma(e, k[i], E.es[i]);
+            }
         }
     }
     const R hc = hh * T.SC[ROW], hh2 = hh * hh;
@@ -773,6 +791,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     EvalPoint<R> x = {y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], y[8], y[9], y[11], y[12], y[13]};
     int stage = kStageF0;
     R h = 0, h_abs = 0, t_new = t;
+    ErrSums<R> esum;              // written by stage_point<6>, read when f(y_new) comes back (unrolled form only)
     R g = y[0];
     int status = -2;
     bool rejected = false;
@@ -798,17 +817,11 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
 #pragma unroll
             for (int i = 0; i < 3; i++) er[i] = 0;
             if constexpr (kUnroll) {
+                // the sums over the six stored stages were formed together with y_new (stage_point<6>)
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const R e = T.E[j], ea = T.EA[j];
+                for (int i = 0; i < kNK; i++) es[i] = esum.es[i];
 #pragma unroll
-                    for (int i = 0; i < kNK; i++) {
-                        if (j == 1 && i >= 3) continue;                       // E[1] = 0: only EA[1] K_1[0..2] counts
-                        const R k = K.get(j, i);
-                        if (j != 1) es[i] = fma(e, k, es[i]);
-                        if (i < 3) er[i] = fma(ea, k, er[i]);
-                    }
-                }
+                for (int i = 0; i < 3; i++) er[i] = esum.er[i];
             } else {
 #pragma unroll 1
                 for (int j = 0; j < 6; j++) {
@@ -931,13 +944,13 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
         // ---- evaluation point of the next RHS call: rk_step (rk.py:58-66) with the row's coefficients ----
         if constexpr (kUnroll) {
             switch (row) {
-            case 1: stage_point<1>(K, y, hh, c.dm, x); break;
-            case 2: stage_point<2>(K, y, hh, c.dm, x); break;
-            case 3: stage_point<3>(K, y, hh, c.dm, x); break;
-            case 4: stage_point<4>(K, y, hh, c.dm, x); break;
-            case 5: stage_point<5>(K, y, hh, c.dm, x); break;
-            case 6: stage_point<6>(K, y, hh, c.dm, x); break;
-            default: stage_point<7>(K, y, hh, c.dm, x); break;
+            case 1: stage_point<1>(K, y, hh, c.dm, x, d, esum); break;
+            case 2: stage_point<2>(K, y, hh, c.dm, x, d, esum); break;
+            case 3: stage_point<3>(K, y, hh, c.dm, x, d, esum); break;
+            case 4: stage_point<4>(K, y, hh, c.dm, x, d, esum); break;
+            case 5: stage_point<5>(K, y, hh, c.dm, x, d, esum); break;
+            case 6: stage_point<6>(K, y, hh, c.dm, x, d, esum); break;
+            default: stage_point<7>(K, y, hh, c.dm, x, d, esum); break;
             }
         } else {
             R acc[kNK], ar0 = 0, ar1 = 0, ar2 = 0;
