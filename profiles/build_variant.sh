@@ -12,7 +12,7 @@ import re, sys
 log = open(f"rl_rocket_6dof_b200/lib/build_{sys.argv[1]}.log").read()
 for m in re.finditer(r"Compiling entry function '(\S+)'.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log):
     name = m.group(1)
-    for k in ("integrate_first_kernelIdLb0", "integrate_resume_kernelIdLb0ELb0", "integrate_resume_kernelIdLb0ELb1", "integrate_kernelIdLb0", "post_kernelId", "step_kernelIdLb0", "tail_kernelId"):
+    for k in ("integrate_first_kernelIdLb0", "integrate_resume_kernelIdLb0ELb0", "integrate_resume_kernelIdLb0ELb1", "integrate_kernelIdLb0", "post_kernelId", "post_pipe_kernelId", "step_kernelIdLb0", "tail_kernelId"):
         if k in name:
             print(f"  {k:32s} regs {m.group(5):>3s}  stack {m.group(2):>4s}  spill st/ld {m.group(3)}/{m.group(4)}")
 PY

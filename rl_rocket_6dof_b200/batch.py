@@ -118,7 +118,10 @@ class Rocket6DOFBatch:
                              else (env_flag != "0" and split_step))
             if multipass and not split_step:
                 raise ValueError("multipass needs the split step (split_step=True)")
-            self.work = torch.zeros(int(self.lib.r6_work_bytes(n)), dtype=torch.uint8, device=dev) if multipass else None
+            self.work = None
+            if multipass:                  # 544 B per env of work records; only the list counters (first 256 B) start at zero
+                self.work = torch.empty(int(self.lib.r6_work_bytes(n)), dtype=torch.uint8, device=dev)
+                self.work[:256].zero_()
             self.t_table = torch.from_numpy(np.ascontiguousarray(params.t_table)).to(dev)
             self.reward_terms = torch.zeros(7, n, dtype=f64, device=dev) if debug_buffers else None
             self.nattempts = torch.zeros(n, dtype=torch.uint8, device=dev) if (debug_buffers or record_attempts) else None

@@ -412,12 +412,60 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
 #define R6_POST_BLOCKS 7         /* resident post-step CTAs per SM (no stage storage: registers are the only limit);
                                     5 (94 registers, no spills) .. 8 (64 registers) measured within 2 % of each other */
 #endif
+#ifndef R6_POST_THREADS
+#define R6_POST_THREADS R6_THREADS
+#endif
+constexpr int kPostThreads = R6_POST_THREADS;
+
+// Everything of the post-step after its inputs are in registers
 template <class R>
-__global__ void __launch_bounds__(kThreads, R6_POST_BLOCKS)
+__device__ __forceinline__ void post_body(const R6Params &p, const R6Buffers &b, const Derived &dv, int64_t n, int64_t i,
+                                          int64_t env_offset, uint64_t seed, EnvT<R> &e, float a0, float a1, float a2, int status,
+                                          int natt)
+{
+    write_obs(b.obs, n, i, p, dv, e.y);          // first thing: the float64 state is then dead but for q and the casts
+    StepOut o;
+    env_post(p, dv, e, a0, a1, a2, status, natt, o);
+    if (b.reward) b.reward[i] = o.reward;
+    if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
+    b.done[i] = o.finished ? 1 : 0;
+    b.flags[i] = (uint8_t)o.flags;
+    if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
+    if (b.status) b.status[i] = (int8_t)o.status;
+    if (b.reward_terms) {
+#pragma unroll
+        for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
+    }
+    if (o.finished) {
+        // rare (one env-step in ~140): the post-step state is read back from `state` (nothing has written it since
+        // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake
+        if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
+        if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
+        if (p.auto_reset) {
+            const R *state = reinterpret_cast<const R *>(b.state);
+            R yt[14];
+#pragma unroll
+            for (int c = 0; c < 14; c++) yt[c] = state[(int64_t)c * n + i];
+            write_obs(b.terminal_obs, n, i, p, dv, yt);
+            write_terminal_state(b, n, i, yt);
+            env_reset(p, b, seed, env_offset + i, e);
+            write_obs(b.obs, n, i, p, dv, e.y);          // replaces the terminal observation written above
+            env_store(b, n, i, e);
+        }
+    }
+    if (!(o.finished && p.auto_reset)) {         // the integrator already stored the state
+        b.step_count[i] = e.k;
+        b.ep_return[i] = e.ep_return;
+        if (b.tgo != nullptr) b.tgo[i] = e.tgo;
+    }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kPostThreads, R6_POST_BLOCKS)
 post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, int64_t env_offset,
             const float *__restrict__ actions, uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
 {
-    const int64_t i = i0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t i = i0 + (int64_t)blockIdx.x * kPostThreads + threadIdx.x;
     if (b.work != nullptr && blockIdx.x == 0 && threadIdx.x < 2)          // the lane's work lists are consumed: empty them
         reinterpret_cast<int32_t *>(b.work)[2 * lane + threadIdx.x] = 0;
     if (i < i1) {
@@ -427,41 +475,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
         else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
         const int status = (int)(int8_t)b.scratch[i], natt = (int)b.scratch[n + i];
-        write_obs(b.obs, n, i, p, dv, e.y);          // first thing: the float64 state is then dead but for q and the casts
-        StepOut o;
-        env_post(p, dv, e, a0, a1, a2, status, natt, o);
-        if (b.reward) b.reward[i] = o.reward;
-        if (b.reward_f32) b.reward_f32[i] = (float)o.reward;
-        b.done[i] = o.finished ? 1 : 0;
-        b.flags[i] = (uint8_t)o.flags;
-        if (b.nattempts) b.nattempts[i] = (uint8_t)o.natt;
-        if (b.status) b.status[i] = (int8_t)o.status;
-        if (b.reward_terms) {
-#pragma unroll
-            for (int k = 0; k < R6_NTERMS; k++) b.reward_terms[(int64_t)k * n + i] = o.post.terms[k];
-        }
-        if (o.finished) {
-            // rare (one env-step in ~140): the post-step state is read back from `state` (nothing has written it since
-            // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake
-            if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
-            if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
-            if (p.auto_reset) {
-                const R *state = reinterpret_cast<const R *>(b.state);
-                R yt[14];
-#pragma unroll
-                for (int c = 0; c < 14; c++) yt[c] = state[(int64_t)c * n + i];
-                write_obs(b.terminal_obs, n, i, p, dv, yt);
-                write_terminal_state(b, n, i, yt);
-                env_reset(p, b, seed, env_offset + i, e);
-                write_obs(b.obs, n, i, p, dv, e.y);          // replaces the terminal observation written above
-                env_store(b, n, i, e);
-            }
-        }
-        if (!(o.finished && p.auto_reset)) {         // the integrator already stored the state
-            b.step_count[i] = e.k;
-            b.ep_return[i] = e.ep_return;
-            if (b.tgo != nullptr) b.tgo[i] = e.tgo;
-        }
+        post_body(p, b, dv, n, i, env_offset, seed, e, a0, a1, a2, status, natt);
     }
     if (b.stats) stats_steps(b.stats, i < i1 ? 1 : 0);
 }
@@ -1026,7 +1040,7 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
             integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
         else
             integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
-        post_kernel<R><<<(unsigned)blocks_for(count), kThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
+        post_kernel<R><<<(unsigned)((count + kPostThreads - 1) / kPostThreads), kPostThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
         return;
     }
     const unsigned g = (unsigned)blocks_for(n);
