@@ -104,7 +104,10 @@ typedef struct R6Params {
     int32_t shaping_velocity;   /* 0 'acceleration', 1 'velocity' */
     int32_t max_episode_steps;  /* TimeLimit; 0 = none */
     int32_t clip_reward;        /* apply ClipReward(clip_lo, clip_hi) to reward[] */
-    int32_t auto_reset;         /* VecEnv semantics: reset finished envs inside the step */
+    int32_t auto_reset;         /* != 0: VecEnv semantics, finished envs are reset inside the step; 0: one-episode semantics
+                                   (evaluate_policy / montecarlo_script.py): an env that finishes keeps done = 1, its terminal
+                                   observation / state / ep_info recorded, and is skipped by every later r6_step* / r6_rollout
+                                   call until r6_reset clears it */
     int32_t n_t;                /* entries in R6Buffers.t_table */
     int32_t obs_rows;           /* rows of obs[] / terminal_obs[] the kernels write: 0 or 14 = all, 13 = RemoveMassFromObs
                                    (saves the mass row when obs[] is mapped host memory) */

@@ -16,15 +16,19 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 gold = os.path.join(root, "tests", "golden", "policy_cl.npz")
 w = policy.load_npz(gold)
 out = {}
-for n in (30, 1 << 20):
+for tk in (False, True):                                   # warm-up: lazy kernel loading, allocator
+    montecarlo.run_montecarlo(1 << 20, w, device="cuda:0", seed=1, tensor_cores=True, two_kernel=tk, lanes=2 if tk else 1)
+for n, kw in ((30, {}), (1 << 20, dict(two_kernel=False)), (1 << 20, dict(two_kernel=True, lanes=2))):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = montecarlo.run_montecarlo(n, w, device="cuda:0", seed=7, tensor_cores=True)
+    res = montecarlo.run_montecarlo(n, w, device="cuda:0", seed=7, tensor_cores=True, **kw)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    out[str(n)] = dict(seconds=dt, mean=res["mean"], std=res["std"], landed=int(res["landed"].sum()),
-                       mean_episode_length=float(res["episode_length"].mean()), env_steps=float(res["stats"]["steps"]))
-    print(n, "episodes in %.2f s" % dt, montecarlo.format_report(res), sep="\n")
+    key = str(n) + ("" if not kw else "_two_kernel" if kw.get("two_kernel") else "_fused")
+    out[key] = dict(seconds=dt, mean=res["mean"], std=res["std"], landed=int(res["landed"].sum()),
+                    mean_episode_length=float(res["episode_length"].mean()), env_steps=float(res["stats"]["steps"]),
+                    env_steps_per_s=float(res["stats"]["steps"]) / dt, mode=kw)
+    print(key, "episodes in %.2f s" % dt, montecarlo.format_report(res), sep="\n")
 g = np.load(gold)
 ends = [int(s) for s in g["ic_step"]][1:] + [len(g["action"])]
 term = np.stack([g["state"][e - 1] for e in ends])

@@ -421,6 +421,7 @@ class Rocket6DOFBatch:
         self.step_count[idx] = step_count
         self.ep_return[idx] = 0
         self.tgo[idx] = 0
+        self.done[idx] = 0          # a new episode: un-freezes the env under one-episode semantics (auto_reset=False)
         self.obs[:, idx] = (self.state[:, idx].to(torch.float64) / torch.as_tensor(self.params.state_normalizer, device=self.device)[:, None]).to(torch.float32)
 
     def get_state(self) -> torch.Tensor:

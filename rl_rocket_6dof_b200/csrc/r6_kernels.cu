@@ -215,7 +215,9 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     KStore<R> K = make_kstore<R>();
     float ob[14];
-    if (i < n) {
+    // one-episode semantics (auto_reset = 0): a finished env stays frozen until r6_reset (obs_row_major implies auto_reset)
+    const bool live = i < n && (p.auto_reset || b.done[i] == 0);
+    if (live) {
         EnvT<R> e;
         env_load(b, n, i, e);
         const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
@@ -234,12 +236,11 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         if (o.finished) {
             if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
             if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
-            if (p.auto_reset) {
-                // DummyVecEnv semantics: keep the terminal observation / state, hand back the reset obs
-                write_obs(b.terminal_obs, n, i, p, dv, e.y);
-                write_terminal_state(b, n, i, e.y);
-                env_reset(p, b, seed, env_offset + i, e);
-            }
+            // keep the terminal observation / state (DummyVecEnv's terminal_observation, montecarlo_script.py:35);
+            // with auto_reset hand back the reset obs
+            write_obs(b.terminal_obs, n, i, p, dv, e.y);
+            write_terminal_state(b, n, i, e.y);
+            if (p.auto_reset) env_reset(p, b, seed, env_offset + i, e);
         }
         if (p.obs_row_major) {
 #pragma unroll
@@ -251,7 +252,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     if (p.obs_row_major)
         write_obs_rows<R>(b.obs, (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31), p.obs_rows > 0 ? p.obs_rows : 14, i < n, ob,
                           K.base - (threadIdx.x & 31));
-    if (b.stats) stats_steps(b.stats, i < n ? 1 : 0);
+    if (b.stats) stats_steps(b.stats, live ? 1 : 0);
 }
 
 // The same env-step as two kernels (used by r6_step when R6Buffers.scratch is given): the divergent, register- and
@@ -268,6 +269,7 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
     KShared<R, kIntThreads> K;
     K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
     if (i >= i1) return;
+    if (!p.auto_reset && b.done[i] != 0) return;      // one-episode semantics: a finished env stays frozen until r6_reset
     R *state = reinterpret_cast<R *>(b.state);
     R y[14];
 #pragma unroll
@@ -341,7 +343,7 @@ integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const flo
     K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
     PassCtx<R> px;
     bool unfinished = false;
-    if (i < i1) {
+    if (i < i1 && (p.auto_reset || b.done[i] == 0)) {       // one-episode semantics: finished envs stay frozen
         R *state = reinterpret_cast<R *>(b.state);
         R y[14];
 #pragma unroll
@@ -441,13 +443,15 @@ __device__ __forceinline__ void post_body(const R6Params &p, const R6Buffers &b,
         // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake
         if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
         if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
-        if (p.auto_reset) {
+        {
             const R *state = reinterpret_cast<const R *>(b.state);
             R yt[14];
 #pragma unroll
             for (int c = 0; c < 14; c++) yt[c] = state[(int64_t)c * n + i];
             write_obs(b.terminal_obs, n, i, p, dv, yt);
             write_terminal_state(b, n, i, yt);
+        }
+        if (p.auto_reset) {
             env_reset(p, b, seed, env_offset + i, e);
             write_obs(b.obs, n, i, p, dv, e.y);          // replaces the terminal observation written above
             env_store(b, n, i, e);
@@ -468,7 +472,8 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     const int64_t i = i0 + (int64_t)blockIdx.x * kPostThreads + threadIdx.x;
     if (b.work != nullptr && blockIdx.x == 0 && threadIdx.x < 2)          // the lane's work lists are consumed: empty them
         reinterpret_cast<int32_t *>(b.work)[2 * lane + threadIdx.x] = 0;
-    if (i < i1) {
+    const bool live = i < i1 && (p.auto_reset || b.done[i] == 0);      // frozen envs (auto_reset = 0, done) are skipped
+    if (live) {
         EnvT<R> e;
         env_load(b, n, i, e);
         float a0, a1, a2;
@@ -477,7 +482,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
         const int status = (int)(int8_t)b.scratch[i], natt = (int)b.scratch[n + i];
         post_body(p, b, dv, n, i, env_offset, seed, e, a0, a1, a2, status, natt);
     }
-    if (b.stats) stats_steps(b.stats, i < i1 ? 1 : 0);
+    if (b.stats) stats_steps(b.stats, live ? 1 : 0);
 }
 
 // k fused steps, state in registers; actions from Philox, a [k][n][3] buffer or the fused policy MLP.

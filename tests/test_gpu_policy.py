@@ -216,6 +216,40 @@ def test_rollout_mlp_needs_weights():
     assert R6Error is not None
 
 
+@pytest.mark.parametrize("two_kernel,tensor_cores,lanes", [(True, False, 1), (True, True, 2)])
+def test_montecarlo_two_kernel_closed_loop_matches_reference_and_fused(two_kernel, tensor_cores, lanes):
+    """Monte-Carlo dispersion (montecarlo_script.py:54-64) through the policy kernel + env-step kernels (one-episode
+    semantics in the split step path: finished envs stay frozen): the reference's 30 recorded closed-loop episodes at
+    the bars of the fused rollout kernel, and a 70 000-episode dispersion equal to the fused kernel's (same Philox
+    initial conditions) up to the amplification of float32 round-off in the actions."""
+    from rl_rocket_6dof_b200 import montecarlo, policy
+    g = np.load(GOLD)
+    w = policy.load_npz(GOLD)
+    starts, ends = _golden_episodes(g)
+    n = len(starts)
+    res = montecarlo.run_montecarlo(n, w, device="cuda:0", ic_table=g["ic"], chunk_steps=64, tensor_cores=tensor_cores,
+                                    two_kernel=two_kernel, lanes=lanes)
+    ref_len = np.array([e - s for s, e in zip(starts, ends)])
+    ref_term = np.stack([g["state"][e - 1] for e in ends])
+    assert np.abs(res["episode_length"] - ref_len).max() <= 1
+    same = res["episode_length"] == ref_len
+    assert same.mean() >= 0.8
+    assert (np.abs(res["terminal_state"] - ref_term) / env_params().state_normalizer)[same].max() <= 2e-3
+    assert res["stats"]["episodes"] == n and res["stats"]["steps"] == res["episode_length"].sum()
+    big = 70_000
+    a = montecarlo.run_montecarlo(big, w, device="cuda:0", seed=5, tensor_cores=tensor_cores, two_kernel=True, lanes=lanes)
+    b = montecarlo.run_montecarlo(big, w, device="cuda:0", seed=5, tensor_cores=tensor_cores, two_kernel=False)
+    assert a["stats"]["episodes"] == b["stats"]["episodes"] == big
+    same = a["episode_length"] == b["episode_length"]
+    print(f"two-kernel vs fused Monte Carlo, {big} episodes: identical lengths {same.mean():.4f}, landed "
+          f"{a['landed'].mean():.4f} / {b['landed'].mean():.4f}")
+    assert same.mean() > 0.97 and np.abs(a["episode_length"] - b["episode_length"]).max() <= 2
+    assert a["stats"]["steps"] == a["episode_length"].sum()
+    for k in a["mean"]:
+        assert abs(a["mean"][k] - b["mean"][k]) <= 2e-3 * abs(b["mean"][k]) + 1e-6, k
+        assert abs(a["std"][k] - b["std"][k]) <= 5e-3 * abs(b["std"][k]) + 1e-6, k
+
+
 @pytest.mark.parametrize("tensor_cores", [False, True])
 def test_closed_loop_montecarlo_matches_reference_episodes(tmp_path, tensor_cores):
     """30 episodes from the reference's own initial conditions, policy in the loop on both sides.
