@@ -81,3 +81,18 @@ def test_build_is_keyed_on_a_source_hash(tmp_path, monkeypatch):
     h0 = b.source_hash()
     monkeypatch.setattr(b, "NVCC_FLAGS", b.NVCC_FLAGS + ["-DSOMETHING"])
     assert b.source_hash() != h0 and b.needs_build()
+
+
+def test_integration_stub_matches_the_library():
+    """The ctypes stub printed in INTEGRATION.md §4: its ABI number and the r6_step / r6_step_range signatures are the
+    library's (the snippet had drifted to an old ABI number)."""
+    from rl_rocket_6dof_b200 import _lib
+    L = _lib.load()
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"assert lib\.r6_abi_version\(\) == (\d+)", text)
+    assert m and int(m.group(1)) == L.r6_abi_version() == _lib.ABI_VERSION
+    assert L.r6_params_size() == C.sizeof(_lib.R6Params) and L.r6_buffers_size() == C.sizeof(_lib.R6Buffers)
+    hdr = open(os.path.join(ROOT, "include", "r6dof.h")).read()
+    sig = re.search(r"int r6_step_range\((.*?)\);", hdr, re.S).group(1)
+    assert len(sig.split(",")) == 11            # p, b, n, first, count, lane, env_offset, actions, seed, step_index, stream
+    assert "r6_step_range(p, b, n, first, count, lane, env_offset, actions, seed, step_index, stream)" in text
