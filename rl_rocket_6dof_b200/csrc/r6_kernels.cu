@@ -810,28 +810,34 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
     using namespace tc5x3;
     extern __shared__ double r6_smem[];
     char *S = reinterpret_cast<char *>(r6_smem);
-    const int tid = threadIdx.x, group = tid >> 7, lt = tid & 127, warp = tid >> 5;
+    const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
     // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
-    for (int idx = tid; idx < 128 * 16; idx += kThreads) {
+    for (int idx = tid; idx < 128 * 16; idx += tc5x3::kThreads) {
         const int r = idx >> 4, k = idx & 15;
         float hi, lo;
         split_tf32(k < kMlpIn ? mlp.w0[r * kMlpIn + k] : 0.0f, hi, lo);
         *reinterpret_cast<float *>(S + kOffW0h + tile_off(r, k, 16)) = hi;
         *reinterpret_cast<float *>(S + kOffW0l + tile_off(r, k, 16)) = lo;
     }
-    for (int idx = tid; idx < 64 * 128; idx += kThreads) {
-        const int r = idx >> 7, k = idx & 127;
-        float hi, lo;
-        split_tf32(mlp.w1[r * kMlpH0 + k], hi, lo);
-        *reinterpret_cast<float *>(S + kOffW1h + tile_off(r, k, 128)) = hi;
-        *reinterpret_cast<float *>(S + kOffW1l + tile_off(r, k, 128)) = lo;
+    // W1 / W2 rows are 16-byte aligned runs of 4 consecutive k = one 16-byte chunk of the canonical tile: vector copies
+    // (the staging is a fixed cost per CTA and launch: 11 264 weights; element-wise it was 9 % of the kernel)
+    for (int idx = tid; idx < 64 * 32; idx += tc5x3::kThreads) {
+        const int r = idx >> 5, k = (idx & 31) * 4;
+        const float4 w = *reinterpret_cast<const float4 *>(mlp.w1 + r * kMlpH0 + k);
+        float4 h, l;
+        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+        *reinterpret_cast<float4 *>(S + kOffW1h + tile_off(r, k, 128)) = h;
+        *reinterpret_cast<float4 *>(S + kOffW1l + tile_off(r, k, 128)) = l;
     }
-    for (int idx = tid; idx < 16 * 64; idx += kThreads) {
-        const int r = idx >> 6, k = idx & 63;
-        float hi, lo;
-        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, hi, lo);
-        *reinterpret_cast<float *>(S + kOffW2h + tile_off(r, k, 64)) = hi;
-        *reinterpret_cast<float *>(S + kOffW2l + tile_off(r, k, 64)) = lo;
+    for (int idx = tid; idx < 16 * 16; idx += tc5x3::kThreads) {
+        const int r = idx >> 4, k = (idx & 15) * 4;
+        float4 h, l;
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, h.x, l.x);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 1) : 0.0f, h.y, l.y);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 2) : 0.0f, h.z, l.z);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 3) : 0.0f, h.w, l.w);
+        *reinterpret_cast<float4 *>(S + kOffW2h + tile_off(r, k, 64)) = h;
+        *reinterpret_cast<float4 *>(S + kOffW2l + tile_off(r, k, 64)) = l;
     }
     float *bias = reinterpret_cast<float *>(S + kOffBias3);
     if (tid < 128) bias[tid] = mlp.b0[tid];
@@ -863,9 +869,9 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
     const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
     for (int64_t tile = 2 * (int64_t)blockIdx.x + group; tile < tiles; tile += 2 * (int64_t)gridDim.x) {
         const int64_t i = po.i0 + tile * kTile + lt;
-        // ---- observations of this thread's env, split -> row `lt` of the input tiles ----
+        // ---- observations of this thread's env, split -> row `lt` of the input tiles (two K-chunks per half) ----
 #pragma unroll
-        for (int kc = 0; kc < 4; kc++) {
+        for (int kc = 2 * half; kc < 2 * half + 2; kc++) {
             float4 h, l;
             split_tf32((4 * kc + 0 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 0) * n + i] : 0.0f, h.x, l.x);
             split_tf32((4 * kc + 1 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 1) * n + i] : 0.0f, h.y, l.y);
@@ -875,27 +881,27 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
             *reinterpret_cast<float4 *>(Hl + tile_off(lt, 4 * kc, 16)) = l;
         }
         fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD0, aHh, aHl, 512, aW0h, aW0l, 512, 2, 128, false); mma_commit(bar); }
+        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD0, aHh, aHl, 512, aW0h, aW0l, 512, 2, 128, false); mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
-        epilogue_to_h3(tmem_row, kColD0, bias, Hh, Hl, lt);
+        epilogue_to_h3(tmem_row, kColD0, bias, Hh, Hl, lt, half);
         fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h, aW1l, 4096, 8, 64, false); mma_commit(bar); }
+        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h, aW1l, 4096, 8, 64, false); mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- second half ----
-        epilogue_to_h3(tmem_row, kColD0 + 64, bias + 64, Hh, Hl, lt);
+        epilogue_to_h3(tmem_row, kColD0 + 64, bias + 64, Hh, Hl, lt, half);
         fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); mma_commit(bar); }
+        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- hidden layer 1 -> output layer ----
-        epilogue_to_h3(tmem_row, kColD1, bias + 128, Hh, Hl, lt);
+        epilogue_to_h3(tmem_row, kColD1, bias + 128, Hh, Hl, lt, half);
         fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0) { fence_after(); issue_mmas3(tmem_g + kColD2, aHh, aHl, 2048, aW2h, aW2l, 2048, 8, 16, false); mma_commit(bar); }
+        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD2, aHh, aHl, 2048, aW2h, aW2l, 2048, 8, 16, false); mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         {
             float v[32];
-            tmem_ld32(tmem_row + kColD2, v);
-            if (i < i1) {
+            if (half == 0) tmem_ld32(tmem_row + kColD2, v);
+            if (half == 0 && i < i1) {
                 const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
                 policy_epilogue(po, mlp.log_std, i, out);
             }
@@ -1221,6 +1227,7 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
     const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
     const unsigned g = (unsigned)(blocks_for(count) < wave ? blocks_for(count) : wave);
     if (tensor_cores == 3) {
+        if ((reinterpret_cast<uintptr_t>(mlp->w1) & 15u) != 0) return fail(R6_EINVAL, "tensor_cores = 3 needs w1 16-byte aligned%s");
         const int64_t pairs = (blocks_for(count) + 1) / 2;                 // one CTA per SM, two tile groups per CTA
         const unsigned g3 = (unsigned)(pairs < sm_count ? pairs : sm_count);
         policy_tc5x3_kernel<<<g3, tc5x3::kThreads, tc5x3::kSmemBytes3, (cudaStream_t)stream>>>(*mlp, obs, n, po);

@@ -151,7 +151,8 @@ __device__ __forceinline__ void issue_mmas(uint32_t d_tmem, uint32_t a_base, uin
 //
 // The split operands need twice the shared memory (weights hi + lo: 88 KB), which rules out two CTAs per SM — and one
 // CTA of four epilogue warps cannot keep the XU / FP32 pipes busy while its MMAs are in flight.  So ONE CTA per SM
-// carries TWO independent 128-env tile groups (warps 0-3 and 4-7) over one resident copy of the weights: each group
+// carries TWO independent 128-env tile groups (warps 0-7 and 8-15; two threads per env row, each taking half of the
+// columns of an epilogue) over one resident copy of the weights: each group
 // has its own activation tiles, TMEM columns, mbarrier and named barrier, its own elected MMA-issuing thread, and walks
 // its own tiles; while one group waits for its MMAs the other is in an epilogue.  The 16-wide input tile aliases the
 // first 8 KB of the group's hidden-activation tile (it is dead once layer 0 has been committed and waited for).
@@ -159,7 +160,8 @@ __device__ __forceinline__ void issue_mmas(uint32_t d_tmem, uint32_t a_base, uin
 //   = 88 + 128 KB + 1 KB;  TMEM: 512 columns, group g at column 256 g: D0 [0,128) D1 [128,192) D2 [192,208).
 namespace tc5x3 {
 using namespace tc5;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;           // two tile groups x (128 rows x 2 column halves)
+constexpr int kGroupThreads = 256;
 constexpr int kOffW0h = 0, kOffW0l = 8 << 10, kOffW1h = 16 << 10, kOffW1l = 48 << 10, kOffW2h = 80 << 10, kOffW2l = 84 << 10;
 constexpr int kOffGroup = 88 << 10, kGroupBytes = 64 << 10, kOffHl = 32 << 10;       // per group: Hh at +0, Hl at +32 KB
 constexpr int kOffBias3 = kOffGroup + 2 * kGroupBytes;                               // b0[128] b1[64] b2[4]
@@ -182,13 +184,14 @@ __device__ __forceinline__ float tanh_f32(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
 }
-__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory"); }
 
-// tanh(D[:, col0 .. col0+63] + bias) of this thread's row, split -> the group's Hh / Hl tiles [128][64]
-__device__ __forceinline__ void epilogue_to_h3(uint32_t tmem_row, uint32_t col0, const float *bias, char *Hh, char *Hl, int row)
+// tanh(D[:, col0 + 32 half .. + 31] + bias) of this thread's row, split -> the group's Hh / Hl tiles [128][64]; the two
+// threads of a row (warps w and w + 4 reach the same 32 TMEM lanes) take 32 of the 64 columns each
+__device__ __forceinline__ void epilogue_to_h3(uint32_t tmem_row, uint32_t col0, const float *bias, char *Hh, char *Hl, int row, int half)
 {
-#pragma unroll
-    for (int cc = 0; cc < 64; cc += 32) {
+    {
+        const int cc = 32 * half;
         float v[32];
         tmem_ld32(tmem_row + col0 + cc, v);
 #pragma unroll
