@@ -109,12 +109,12 @@ class Rocket6DOFBatch:
             self._lanes_pending = False
             self.scratch = torch.zeros(2, n, dtype=torch.uint8, device=dev) if split_step else None
             # multi-pass integrator (R6Buffers.work): one RK attempt per pass, unfinished envs compacted into work
-            # lists for the next pass; on with the float64 kernel pair for large batches unless asked otherwise (+4 %
-            # at 2^20 envs, +6 % beyond; below 2^19 the four small launches cost more than the idle lanes did; the
-            # float32 integrator is issue-bound and loses 1.5 % to the extra passes) — profiles/r01_sweep_envs_v11*
+            # lists for the next pass; on with the kernel pair for large batches unless asked otherwise (below 2^19 envs
+            # the four small launches cost more than the idle lanes did).  Round 2: with the one-attempt pass kernels it
+            # also pays on the float32 path (0.263 -> 0.236 ms per 2^20-env step) — profiles/r02_fp32_multipass.txt
             if multipass is None:
                 env_flag = os.environ.get("R6_MULTIPASS")
-                multipass = ((split_step and precision == "fp64" and n >= MULTIPASS_MIN_ENVS) if env_flag is None
+                multipass = ((split_step and n >= MULTIPASS_MIN_ENVS) if env_flag is None
                              else (env_flag != "0" and split_step))
             if multipass and not split_step:
                 raise ValueError("multipass needs the split step (split_step=True)")

@@ -14,7 +14,9 @@ from parity_utils import env_params
 pytestmark = pytest.mark.gpu
 
 
-def test_fp32_path_tracks_fp64_path():
+@pytest.mark.parametrize("multipass", [False, True])
+def test_fp32_path_tracks_fp64_path(multipass):
+    """multipass=True: the dispatch large float32 batches take by default (one RK attempt per pass, two stream lanes)."""
     import torch
     from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
     ep = env_params()
@@ -22,7 +24,7 @@ def test_fp32_path_tracks_fp64_path():
     kw = dict(params=ep, device="cuda:0", auto_reset=False, clip_reward=False, time_limit=False, seed=21,
               record_attempts=True)
     a = Rocket6DOFBatch(n, precision="fp64", **kw)
-    b = Rocket6DOFBatch(n, precision="fp32", **kw)
+    b = Rocket6DOFBatch(n, precision="fp32", **(dict(kw, split_step=True, multipass=True, lanes=2) if multipass else kw))
     a.reset(); b.reset()
     assert b.state.dtype == torch.float32 and b.terminal_state.dtype == torch.float32
     assert torch.equal(a.state.to(torch.float32), b.state)          # same Philox initial conditions
