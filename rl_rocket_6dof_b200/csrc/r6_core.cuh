@@ -376,18 +376,6 @@ __constant__ RhoStep kRhoStepDev = make_rho_step();
 R6_HD double rho_b(int k, double) { return R6_RHO_STEP.b[k]; }
 R6_HD float rho_b(int k, float) { return R6_RHO_STEP.bf[k]; }
 
-template <bool kExact, class R>
-R6_HD R density(const StepConstT<R> &c, R h)
-{
-    if (kExact) return density_exact(h);
-    const R d = c.kd * (h - c.h0);
-    // float: d^4 and beyond are below the rounding of the sum (|d| <= 0.01)
-    R s = (sizeof(R) == 8) ? fma(fma(fma(rho_b(6, R()), d, rho_b(5, R())), d, rho_b(4, R())), d, rho_b(3, R())) : rho_b(3, R());
-    s = fma(s, d, rho_b(2, R()));
-    s = fma(s, d, rho_b(1, R()));
-    s = fma(s, d, R(1.0));
-    return c.rho0 * s;
-}
 constexpr double kMaxDtSeries = 0.25;   // (1000 m/s + 60 m/s^2 dt) dt kd <= 0.01 up to here
 
 // folded per-step constants of rhs() from (Tb, Ji1, w0)
