@@ -517,26 +517,53 @@ R6_HD bool sgn(float x) { return signbit(x); }
 // host (tests/hostsim) in a local array.
 constexpr int kNK = 9;   // stored components per stage
 template <class R>
+struct Pair {
+    R a, b;
+};
+template <class R>
 struct KLocalT {
     R k[6][kNK];
     R6_HD R get(int j, int c) const { return k[j][c]; }
     R6_HD void set(int j, int c, R v) { k[j][c] = v; }
+    R6_HD Pair<R> get2(int j, int p) const { return Pair<R>{k[j][2 * p], k[j][2 * p + 1]}; }
+    R6_HD void set2(int j, int p, R a, R b) { k[j][2 * p] = a; k[j][2 * p + 1] = b; }
 };
 using KLocal = KLocalT<double>;
 #if defined(__CUDACC__)
+// [stage][pair][thread][2] for components 0..7 and [stage][8][thread] for the ninth: a thread's components 2p, 2p+1 are
+// adjacent, so a pair moves with ONE 128-bit (float64) shared-memory instruction; a warp's 32 pairs are 512 contiguous
+// bytes (conflict-free in four wavefronts, the same data-pipe time as two 64-bit accesses, half the issue slots).
 template <class R, int kThreadsPerBlock>
 struct KShared {
-    R *base;   // smem + threadIdx.x
-    __device__ __forceinline__ R get(int j, int c) const { return base[(j * kNK + c) * kThreadsPerBlock]; }
-    __device__ __forceinline__ void set(int j, int c, R v) { base[(j * kNK + c) * kThreadsPerBlock] = v; }
+    R *base;   // smem + 2 * threadIdx.x
+    __device__ __forceinline__ int off(int j, int c) const
+    {
+        return j * kNK * kThreadsPerBlock + (c < 8 ? (c >> 1) * 2 * kThreadsPerBlock + (c & 1) : 8 * kThreadsPerBlock - (int)threadIdx.x);
+    }
+    __device__ __forceinline__ R get(int j, int c) const { return base[off(j, c)]; }
+    __device__ __forceinline__ void set(int j, int c, R v) { base[off(j, c)] = v; }
+    __device__ __forceinline__ Pair<R> get2(int j, int p) const
+    {
+        if constexpr (sizeof(R) == 8) {
+            const double2 v = *reinterpret_cast<const double2 *>(base + (j * kNK + 2 * p) * kThreadsPerBlock);
+            return Pair<R>{v.x, v.y};
+        } else {
+            const float2 v = *reinterpret_cast<const float2 *>(base + (j * kNK + 2 * p) * kThreadsPerBlock);
+            return Pair<R>{v.x, v.y};
+        }
+    }
+    __device__ __forceinline__ void set2(int j, int p, R a, R b)
+    {
+        if constexpr (sizeof(R) == 8) *reinterpret_cast<double2 *>(base + (j * kNK + 2 * p) * kThreadsPerBlock) = make_double2(a, b);
+        else *reinterpret_cast<float2 *>(base + (j * kNK + 2 * p) * kThreadsPerBlock) = make_float2(a, b);
+    }
 };
 #endif
 template <class KS, class R>
 R6_HD void k_store(KS &K, int j, const DerivT<R> &d)
 {
-    K.set(j, 0, d.dv0); K.set(j, 1, d.dv1); K.set(j, 2, d.dv2);
-    K.set(j, 3, d.dq0); K.set(j, 4, d.dq1); K.set(j, 5, d.dq2); K.set(j, 6, d.dq3);
-    K.set(j, 7, d.dw1); K.set(j, 8, d.dw2);
+    K.set2(j, 0, d.dv0, d.dv1); K.set2(j, 1, d.dv2, d.dq0); K.set2(j, 2, d.dq1, d.dq2); K.set2(j, 3, d.dq3, d.dw1);
+    K.set(j, 8, d.dw2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,10 +728,21 @@ R6_HD void stage_point(const KS &K, const R *y, R hh, R dm, EvalPoint<R> &x, con
         const R a = T.SA[ROW][j], aa = T.SAA[ROW][j];
         const R e = kErr ? T.E[j] : R(0), ea = kErr ? T.EA[j] : R(0);
         R k[kNK];
+        if (newest) {
 #pragma unroll
-        for (int i = 0; i < kNK; i++) {
-            const bool needed = !skip_a || (i == 0 && kPos) || (i < 3 && kHoriz);
-            k[i] = !needed ? R(0) : (newest ? dnv[i] : K.get(j, i));
+            for (int i = 0; i < kNK; i++) k[i] = dnv[i];
+        } else if (skip_a) {                              // velocity components only (position sums of y_new)
+            const Pair<R> p0 = K.get2(j, 0), p1 = K.get2(j, 1);
+            k[0] = p0.a; k[1] = p0.b; k[2] = p1.a;
+#pragma unroll
+            for (int i = 3; i < kNK; i++) k[i] = 0;
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const Pair<R> v = K.get2(j, p);
+                k[2 * p] = v.a; k[2 * p + 1] = v.b;
+            }
+            k[8] = K.get(j, 8);
         }
         // j = 0 starts the sums with a product (no zeroed accumulators); SAA[ROW][0] = 0 only for ROW = 1 and 7
         if (kPos) ar0 = j == 0 ? aa * k[0] : fma(aa, k[0], ar0);
@@ -1202,11 +1240,13 @@ R6_HD double div_exact(double a, double b, double rinv)
     const double rem = fma(-q, b, a);
     return fma(rem, rinv, q);
 }
-R6_HD float obs_component(const R6Params &p, const Derived &dv, const double *y, int i)
+R6_HD float obs_scalar(const R6Params &p, const Derived &dv, double yi, int i)
 {
-    return f64_to_f32(div_exact(y[i], p.normalizer[i], dv.inv_norm[i]));
+    return f64_to_f32(div_exact(yi, p.normalizer[i], dv.inv_norm[i]));
 }
-R6_HD float obs_component(const R6Params &, const Derived &dv, const float *y, int i) { return y[i] * dv.inv_norm_f[i]; }
+R6_HD float obs_scalar(const R6Params &, const Derived &dv, float yi, int i) { return yi * dv.inv_norm_f[i]; }
+template <class R>
+R6_HD float obs_component(const R6Params &p, const Derived &dv, const R *y, int i) { return obs_scalar(p, dv, y[i], i); }
 
 // Extrinsic zyx Euler angles of the float32-cast quaternion (scipy _rotation_xp.py:365-401,
 // 1052-1111), reduced to what the env needs: the two limit tests.  With a = w-y, b = z-x, c = y+w,

@@ -85,9 +85,9 @@ template <class R> using KStore = KShared<R, kThreads>;
 template <class R>
 __device__ __forceinline__ KStore<R> make_kstore()
 {
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     KStore<R> K;
-    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     return K;
 }
 
@@ -180,19 +180,22 @@ reset_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, i
 }
 
 // Row-major observation block of one warp: the 32 x rows floats of the warp's envs are contiguous in a [n][rows]
-// array.  Each lane parks its row in the warp's (by now dead) stage-storage columns, then the warp streams the block
-// out with fully coalesced 128-byte stores.  Warp-collective: call with every lane, `valid` = this lane has an env.
+// array.  Each lane parks its row in the warp's (by now dead) stage storage, then the warp streams the block out with
+// fully coalesced 128-byte stores.  Warp-collective: call with every lane, `valid` = this lane has an env.
+// Staging slot of (component c, lane l): the first 32 entries of the warp's span of pair row (stage c / 4, pair c % 4)
+// — with the paired stage layout a warp owns [2 w0, 2 w0 + 64) of every pair row, w0 = its first thread.
 template <class R>
 __device__ __forceinline__ void write_obs_rows(float *obs, int64_t first_env, int rows, bool valid, const float (&ob)[14],
-                                               R *stage_warp /* smem + first thread of the warp */)
+                                               R *smem /* the CTA's stage storage */)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+    auto slot = [&](int c, int l) { return reinterpret_cast<float *>(&smem[(kNK * (c >> 2) + 2 * (c & 3)) * kThreads + 2 * w0 + l]); };
     const unsigned live = __ballot_sync(0xffffffffu, valid);
     const int n_valid = __popc(live);                       // valid lanes are a prefix (contiguous env indices)
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 14; c++)
-        if (c < rows) *reinterpret_cast<float *>(&stage_warp[c * kThreads + lane]) = ob[c];
+        if (c < rows) *slot(c, lane) = ob[c];
     __syncwarp();
     float *dst = obs + first_env * rows;
     const int total = n_valid * rows;
@@ -201,7 +204,7 @@ __device__ __forceinline__ void write_obs_rows(float *obs, int64_t first_env, in
         const int el = lane + 32 * k;
         if (k < rows && el < total) {
             const int env = el / rows, c = el - env * rows;
-            dst[el] = *reinterpret_cast<const float *>(&stage_warp[c * kThreads + env]);
+            dst[el] = *slot(c, env);
         }
     }
     __syncwarp();
@@ -251,7 +254,7 @@ step_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
     }
     if (p.obs_row_major)
         write_obs_rows<R>(b.obs, (int64_t)blockIdx.x * kThreads + (threadIdx.x & ~31), p.obs_rows > 0 ? p.obs_rows : 14, i < n, ob,
-                          K.base - (threadIdx.x & 31));
+                          K.base - 2 * threadIdx.x);
     if (b.stats) stats_steps(b.stats, live ? 1 : 0);
 }
 
@@ -265,9 +268,9 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
                  uint64_t seed, int64_t step_index, int64_t i0, int64_t i1)
 {
     const int64_t i = i0 + (int64_t)blockIdx.x * kIntThreads + threadIdx.x;     // this launch steps envs [i0, i1)
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     KShared<R, kIntThreads> K;
-    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     if (i >= i1) return;
     if (!p.auto_reset && b.done[i] != 0) return;      // one-episode semantics: a finished env stays frozen until r6_reset
     R *state = reinterpret_cast<R *>(b.state);
@@ -338,9 +341,9 @@ integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const flo
                        uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
 {
     const int64_t i = i0 + (int64_t)blockIdx.x * kIntThreads + threadIdx.x;
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     KShared<R, kIntThreads> K;
-    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     PassCtx<R> px;
     bool unfinished = false;
     if (i < i1 && (p.auto_reset || b.done[i] == 0)) {       // one-episode semantics: finished envs stay frozen
@@ -373,9 +376,9 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
 {
     constexpr int src = kLast ? 1 : 0;
     constexpr int budget = kLast ? (1 << 30) : 1;
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     KShared<R, kIntThreads> K;
-    K.base = reinterpret_cast<R *>(r6_smem) + threadIdx.x;
+    K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     const WorkView W = work_view(b.work, n);
     const int64_t cnt = W.count[2 * lane + src];
     R *state = reinterpret_cast<R *>(b.state);
@@ -440,21 +443,27 @@ __device__ __forceinline__ void post_body(const R6Params &p, const R6Buffers &b,
     }
     if (o.finished) {
         // rare (one env-step in ~140): the post-step state is read back from `state` (nothing has written it since
-        // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake
+        // the integrator) so that the 14 doubles are not kept alive through the reward code for this path's sake.
+        // (Moving this path out of line into a __noinline__ function cost 5-8 us: measured, rejected.)
         if (b.stats) stats_episode<R>(b.stats, o.flags, e.ep_return, e.k);
         if (b.ep_info) { b.ep_info[i] = e.ep_return; b.ep_info[n + i] = (double)e.k; }
-        {
-            const R *state = reinterpret_cast<const R *>(b.state);
+        const R *state = reinterpret_cast<const R *>(b.state);
+        if (p.auto_reset) {
             R yt[14];
 #pragma unroll
             for (int c = 0; c < 14; c++) yt[c] = state[(int64_t)c * n + i];
             write_obs(b.terminal_obs, n, i, p, dv, yt);
             write_terminal_state(b, n, i, yt);
-        }
-        if (p.auto_reset) {
             env_reset(p, b, seed, env_offset + i, e);
             write_obs(b.obs, n, i, p, dv, e.y);          // replaces the terminal observation written above
             env_store(b, n, i, e);
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < 14; c++) {               // one-episode semantics: record the terminal state / observation
+                const R yc = state[(int64_t)c * n + i];
+                reinterpret_cast<R *>(b.terminal_state)[(int64_t)c * n + i] = yc;
+                if (c < (p.obs_rows > 0 ? p.obs_rows : 14)) b.terminal_obs[(int64_t)c * n + i] = obs_scalar(p, dv, yc, c);
+            }
         }
     }
     if (!(o.finished && p.auto_reset)) {         // the integrator already stored the state
@@ -500,7 +509,7 @@ rollout_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n,
     const float *W = nullptr;
     if (kMode == R6_ACT_MLP) {
         // pack the policy weights into shared memory once per CTA (transposes W1, pads W0 rows)
-        extern __shared__ double r6_smem[];
+        extern __shared__ __align__(16) double r6_smem[];
         float *Ws = reinterpret_cast<float *>(reinterpret_cast<char *>(r6_smem) + smem_bytes<R>());
         for (int idx = threadIdx.x; idx < kMlpFloats; idx += kThreads) Ws[idx] = mlp_pack_element(mlp, idx);
         __syncthreads();
@@ -572,7 +581,7 @@ rollout_tc_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     KStore<R> K = make_kstore<R>();
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     float *Ws = reinterpret_cast<float *>(reinterpret_cast<char *>(r6_smem) + smem_bytes<R>());
     for (int idx = threadIdx.x; idx < kMlpTcFloats; idx += kThreads) Ws[idx] = mlp_tc_pack_element(mlp, idx);
     __syncthreads();
@@ -693,7 +702,7 @@ template <bool kTc>
 __global__ void __launch_bounds__(kThreads, kTc ? 3 : 4)
 policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     float *Ws = reinterpret_cast<float *>(r6_smem);
     const int nW = kTc ? kMlpTcFloats : kMlpFloats;
     for (int idx = threadIdx.x; idx < nW; idx += kThreads) Ws[idx] = kTc ? mlp_tc_pack_element(mlp, idx) : mlp_pack_element(mlp, idx);
@@ -718,7 +727,7 @@ __global__ void __launch_bounds__(tc5::kTile, 2)
 policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
     using namespace tc5;
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     char *S = reinterpret_cast<char *>(r6_smem);
     const int tid = threadIdx.x, warp = tid >> 5;
     // ---- one-time per CTA: weights (TF32-rounded) into canonical K-major tiles, biases, barrier, TMEM ----
@@ -808,7 +817,7 @@ __global__ void __launch_bounds__(tc5x3::kThreads, 1)
 policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
     using namespace tc5x3;
-    extern __shared__ double r6_smem[];
+    extern __shared__ __align__(16) double r6_smem[];
     char *S = reinterpret_cast<char *>(r6_smem);
     const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
     // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
