@@ -129,6 +129,28 @@ def test_nan_env_does_not_disturb_neighbours():
     assert torch.equal(a.state[:, keep], b.state[:, keep]) and torch.equal(a.reward[keep], b.reward[keep])
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_no_tgo_root_keeps_reward_and_statistics_finite(split):
+    """r = 0 exactly: the t_go quartic g^2 t^4 - 4 |v|^2 t^2 has no constant term and the reference raises IndexError
+    (rocket_env.py:545).  The kernels define the target acceleration as that of t_go -> infinity instead, so the reward
+    is finite and one such env cannot poison the batch statistics (a NaN return went into the shared sums)."""
+    import torch
+    n = 300
+    env = _mk(n, auto_reset=True, split_step=split, seed=4)
+    env.reset()
+    ic = env.state.t().clone().to(torch.float32)
+    ic[7, 0:3] = 0.0                                     # env 7 sits exactly at the origin, moving
+    env.set_state(ic[7:8], torch.tensor([7]))
+    acts = torch.zeros(n, 3, device="cuda")
+    env.step(acts)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(env.reward).all()) and bool(torch.isfinite(env.ep_return).all())
+    env.rollout(400)                                      # every env finishes at least one episode
+    torch.cuda.synchronize()
+    s = env.stats.cpu().numpy()
+    assert np.all(np.isfinite(s)) and s[0] >= n
+
+
 def test_step_random_equals_fused_rollout():
     """r6_step_random (integrator | post-step kernels, in-kernel Philox) == r6_rollout(R6_ACT_PHILOX), step by step."""
     import torch

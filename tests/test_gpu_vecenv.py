@@ -70,6 +70,7 @@ def test_vecenv_protocol_and_infos():
             assert set(info) >= {"terminal_observation", "episode", "TimeLimit.truncated", "state_history"}
             assert info["episode"]["l"] == length[i]
             assert abs(info["episode"]["r"] - ret[i]) <= 1e-3 * max(1.0, abs(ret[i]))
+            assert info["episode"]["r"] == round(info["episode"]["r"], 6)      # Monitor: float64 sum rounded to 6 decimals
             ts = info["state_history"][-1]
             assert ts.shape == (14,)
             tob = (ts / norm).astype(np.float32)[:13]
@@ -82,6 +83,7 @@ def test_vecenv_protocol_and_infos():
             length[i] = 0
         for i in np.nonzero(~dones)[0][:4]:
             assert infos[i] == {}
+            infos[i]["scribble"] = j                      # a wrapper writing into an info dict must not leak into later steps
     assert finished >= n
     env.close()
 
