@@ -23,7 +23,8 @@ F_EVENT, F_OOB, F_TRUNCATED = 0x01, 0x02, 0x04
 F_LANDING_ALL = 0xF8
 FLAG_NAMES = ["zero_height", "velocity_limit", "landing_radius", "attitude_limit", "omega_limit"]
 SPLIT_MIN_ENVS = 65536
-MULTIPASS_MIN_ENVS = 1 << 19   # smallest batch the multi-pass integrator is the default for (float64 kernel pair)
+MULTIPASS_MIN_ENVS = 1 << 18   # smallest batch the multi-pass integrator is the default for (float64; float32: twice that)
+#                                (profiles/r02_sweep_dispatch.json: 2^18 envs, two lanes: 120 vs 129 us per step)
 STAT_NAMES = ["episodes", "return_sum", "length_sum", "landed", "ground", "out_of_bounds", "truncated", "steps"]
 
 
@@ -114,7 +115,7 @@ class Rocket6DOFBatch:
             # also pays on the float32 path (0.263 -> 0.236 ms per 2^20-env step) — profiles/r02_fp32_multipass.txt
             if multipass is None:
                 env_flag = os.environ.get("R6_MULTIPASS")
-                multipass = ((split_step and n >= MULTIPASS_MIN_ENVS) if env_flag is None
+                multipass = ((split_step and n >= MULTIPASS_MIN_ENVS * (2 if precision == "fp32" else 1)) if env_flag is None
                              else (env_flag != "0" and split_step))
             if multipass and not split_step:
                 raise ValueError("multipass needs the split step (split_step=True)")
