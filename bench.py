@@ -41,7 +41,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--preroll", type=int, default=256, help="untimed env-steps to reach the steady-state episode mix")
+    ap.add_argument("--preroll", type=int, default=1024,
+                    help="untimed env-steps to reach the stationary mix of episode phases: all envs start their first episode "
+                         "together and episodes last 143 +- 31 steps, so the step time keeps oscillating by +-4 %% with the "
+                         "share of envs that finish per step until ~1000 steps in (profiles/r02_preroll_scan.txt)")
     ap.add_argument("--lanes", type=int, default=2, help="CUDA streams each GPU's env range is stepped on (r6_step_range)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=32768)
