@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--tag", default=os.environ.get("R6_LIB_PATH", "default"))
 ap.add_argument("--no-prof", action="store_true")
 ap.add_argument("--precision", default="fp64")
+ap.add_argument("--preroll", type=int, default=256)
 ap.add_argument("--multipass", type=int, default=-1, help="-1 auto, 0 off, 1 on")
 a = ap.parse_args()
 n, K = a.envs, a.steps
@@ -47,7 +48,7 @@ for lanes in (2, 1):
     env = Rocket6DOFBatch(n, device="cuda:0", seed=42, lanes=lanes, record_attempts=True, precision=a.precision,
                           split_step=True, multipass=None if a.multipass < 0 else bool(a.multipass))
     env.reset()
-    env.rollout(256)
+    env.rollout(a.preroll)
     if lanes == 2:
         out["lanes2_joined_ms"] = min(timed(env, True, K) for _ in range(2))
         out["lanes2_free_ms"] = min(timed(env, False, K) for _ in range(2))
