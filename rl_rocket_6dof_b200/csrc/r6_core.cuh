@@ -790,7 +790,7 @@ R6_HD void stage_point(const KS &K, const R *y, R hh, R dm, EvalPoint<R> &x, con
 // (same inputs, same instructions => the same bits).  kPass = 0 is the single-call form.
 template <class R>
 struct PassCtx {
-    R t, h_abs, h_ref;
+    R t, h_abs, h_ref, t_bound;     // t_bound rides along so that a resumed pass needs neither step_count nor the time table
     int natt, budget;
     bool rejected;
 };
@@ -809,7 +809,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     // their hot footprint (integrator + reward + reset in one kernel) is what the instruction cache bounds, and the
     // unrolled rows (+10 KB) cost them 7 % (rollout_fused 1.73e9 -> 1.61e9 env-steps/s).  Same arithmetic either way.
     constexpr bool kUnroll = R6_ROWS_UNROLLED != 0 && kPass != 0;
-    const R t_bound = t + dt;
+    const R t_bound = kPass == 2 ? px.t_bound : t + dt;
     const R L = fabs(t_bound - t);                       // common.py:100 (interval length as SciPy computes it)
     if constexpr (kPass == 2) density_setup(c, px.h_ref);
     else density_setup(c, y[0]);
@@ -824,7 +824,7 @@ R6_HD int integrate(StepConstT<R> &c, R *y, R t, R dt, int &natt, KS &K, PassCtx
     natt = 0;
     int budget = 0;
     if constexpr (kPass != 0) budget = px.budget;
-    if constexpr (kPass == 1) px.h_ref = y[0];
+    if constexpr (kPass == 1) { px.h_ref = y[0]; px.t_bound = t_bound; }
     if constexpr (kPass == 2) { t = px.t; t_new = t; h_abs = px.h_abs; rejected = px.rejected; natt = px.natt; }
     for (;;) {
         const DerivT<R> d = rhs<kExact>(c, x.h, x.v0, x.v1, x.v2, x.q0, x.q1, x.q2, x.q3, x.w1, x.w2, x.m);
@@ -1707,7 +1707,7 @@ R6_HD int env_integrate_pass(const R6Params &p, const double *__restrict__ t_tab
     StepConstT<R> c;
     consts_env_mode(c, m0, u0, u1, u2, y[10]);
     R t = 0;
-    if constexpr (sizeof(R) == 8) {
+    if constexpr (sizeof(R) == 8 && kPass != 2) {          // a resumed pass carries its own clock (px.t, px.t_bound)
         const int kk = k < p.n_t ? k : p.n_t - 1;
         t = (R)t_table[kk];
     }

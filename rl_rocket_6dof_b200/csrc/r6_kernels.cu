@@ -303,7 +303,7 @@ struct WorkView {
     int32_t *count;          // [2 * kMaxLanes] entries of list l of lane a: count[2 a + l]
     int32_t *list[2];        // [n] env index; a range [i0, i1) uses the slots [i0, i1) of each array
     int32_t *meta[2];        // [n] attempts | rejected << 8
-    double *ctx[2];          // [3][n] t, h_abs, h_ref
+    double *ctx[2];          // [4][n] t, h_abs, h_ref, t_bound
 };
 __host__ __device__ inline WorkView work_view(uint8_t *w, int64_t n)
 {
@@ -312,7 +312,7 @@ __host__ __device__ inline WorkView work_view(uint8_t *w, int64_t n)
     int32_t *q = reinterpret_cast<int32_t *>(w + 256);
     v.list[0] = q; v.list[1] = q + n; v.meta[0] = q + 2 * n; v.meta[1] = q + 3 * n;
     double *d = reinterpret_cast<double *>(w + 256 + 16 * n);
-    v.ctx[0] = d; v.ctx[1] = d + 3 * n;
+    v.ctx[0] = d; v.ctx[1] = d + 4 * n;
     return v;
 }
 
@@ -332,6 +332,7 @@ __device__ __forceinline__ void work_append(const WorkView &W, int64_t n, int ds
         W.meta[dst][slot] = px.natt | (px.rejected ? 256 : 0);
         double *c = W.ctx[dst];
         c[slot] = (double)px.t; c[n + slot] = (double)px.h_abs; c[2 * n + slot] = (double)px.h_ref;
+        c[3 * n + slot] = (double)px.t_bound;
     }
 }
 
@@ -392,6 +393,7 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
             const int meta = W.meta[src][i0 + slot];
             const double *c = W.ctx[src];
             px.t = (R)c[i0 + slot]; px.h_abs = (R)c[n + i0 + slot]; px.h_ref = (R)c[2 * n + i0 + slot];
+            px.t_bound = (R)c[3 * n + i0 + slot];
             px.natt = meta & 255; px.rejected = (meta & 256) != 0; px.budget = budget;
             R y[14];
 #pragma unroll
@@ -400,7 +402,7 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
             if (actions != nullptr) { a0 = actions[3 * i]; a1 = actions[3 * i + 1]; a2 = actions[3 * i + 2]; }
             else philox_action(seed, (uint64_t)(env_offset + i), (uint64_t)step_index, a0, a1, a2);
             int natt;
-            const int status = env_integrate_pass<kExact, 2>(p, b.t_table, y, b.m0[i], b.step_count[i], a0, a1, a2, K, px, natt);
+            const int status = env_integrate_pass<kExact, 2>(p, b.t_table, y, b.m0[i], 0, a0, a1, a2, K, px, natt);
 #pragma unroll
             for (int cc = 0; cc < 14; cc++) state[(int64_t)cc * n + i] = y[cc];
             unfinished = status == -2;
@@ -1149,7 +1151,7 @@ int r6_step_random(const R6Params *p, const R6Buffers *b, int64_t n, int64_t env
     return check_launch("r6_step_random");
 }
 
-int64_t r6_work_bytes(int64_t n) { return n < 0 ? 0 : 256 + 64 * n; }
+int64_t r6_work_bytes(int64_t n) { return n < 0 ? 0 : 256 + 80 * n; }
 
 int r6_step_range(const R6Params *p, const R6Buffers *b, int64_t n, int64_t first, int64_t count, int32_t lane,
                   int64_t env_offset, const float *actions, uint64_t seed, int64_t step_index, void *stream)
