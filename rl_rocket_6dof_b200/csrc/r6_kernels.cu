@@ -925,6 +925,168 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols3) : "memory");
 }
 
+// The same policy with the activations kept in tensor memory (A operand of tcgen05.mma read from TMEM; see namespace
+// tc5ts in r6_mlp_tcgen05.cuh): the kernel r6_policy(tensor_cores = 3) launches.
+#ifndef R6_POLICY_TS
+#define R6_POLICY_TS 1
+#endif
+#ifndef R6_TS_PINGPONG
+#define R6_TS_PINGPONG 1
+#endif
+// Epilogue token of the two tile groups (named barriers 3 and 4, 512 participants: the 256 threads of the group that
+// takes the token bar.sync, the 256 of the group that hands it over bar.arrive).  Only one group at a time is in a
+// bias + tanh + split epilogue (the XU / FP32 phase); the other group's MMAs run underneath it.  Without it the two
+// groups fall into lock-step — both in an epilogue fighting for the XU pipe, then both waiting on the tensor pipe.
+__device__ __forceinline__ void token_take(int group)
+{
+#if R6_TS_PINGPONG
+    asm volatile("bar.sync %0, 512;" ::"r"(group + 3) : "memory");
+#endif
+}
+__device__ __forceinline__ void token_pass(int to_group)
+{
+#if R6_TS_PINGPONG
+    asm volatile("bar.arrive %0, 512;" ::"r"(to_group + 3) : "memory");
+#endif
+}
+__global__ void __launch_bounds__(tc5x3::kThreads, 1)
+policy_tc5ts_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
+{
+    using namespace tc5ts;
+    extern __shared__ __align__(16) double r6_smem[];
+    char *S = reinterpret_cast<char *>(r6_smem);
+    const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
+    // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
+    for (int idx = tid; idx < 128 * 16; idx += tc5x3::kThreads) {
+        const int r = idx >> 4, k = idx & 15;
+        float hi, lo;
+        split_tf32(k < kMlpIn ? mlp.w0[r * kMlpIn + k] : 0.0f, hi, lo);
+        *reinterpret_cast<float *>(S + kOffW0h + tile_off(r, k, 16)) = hi;
+        *reinterpret_cast<float *>(S + kOffW0l + tile_off(r, k, 16)) = lo;
+    }
+    for (int idx = tid; idx < 64 * 32; idx += tc5x3::kThreads) {
+        const int r = idx >> 5, k = (idx & 31) * 4;
+        const float4 w = *reinterpret_cast<const float4 *>(mlp.w1 + r * kMlpH0 + k);
+        float4 h, l;
+        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+        *reinterpret_cast<float4 *>(S + kOffW1h + tile_off(r, k, 128)) = h;
+        *reinterpret_cast<float4 *>(S + kOffW1l + tile_off(r, k, 128)) = l;
+    }
+    for (int idx = tid; idx < 16 * 16; idx += tc5x3::kThreads) {
+        const int r = idx >> 4, k = (idx & 15) * 4;
+        float4 h, l;
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, h.x, l.x);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 1) : 0.0f, h.y, l.y);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 2) : 0.0f, h.z, l.z);
+        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 3) : 0.0f, h.w, l.w);
+        *reinterpret_cast<float4 *>(S + kOffW2h + tile_off(r, k, 64)) = h;
+        *reinterpret_cast<float4 *>(S + kOffW2l + tile_off(r, k, 64)) = l;
+    }
+    float *bias = reinterpret_cast<float *>(S + kOffBiasT);
+    if (tid < 128) bias[tid] = mlp.b0[tid];
+    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
+    if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBarT)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBarT + 8)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtrT)), "n"(kTmemCols3) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();                      // the weight tiles are read by the async proxy (MMA B operand)
+    fence_before();
+    __syncthreads();
+    fence_after();
+    // warp-uniform copies (a shuffle result is uniform to the compiler) of everything the MMA-issuing warp computes with
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtrT), 0);
+    const uint32_t tmem_g = tmem_base + (uint32_t)(warp_u >> 3) * kGroupCols;              // this group's columns, lane 0
+    const uint32_t tmem_row = tmem_g + ((uint32_t)((warp & 3) * 32) << 16);                // this warp's 32 TMEM lanes
+    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(S), 0);
+    const uint32_t aW0h = sbase + kOffW0h, aW0l = sbase + kOffW0l, aW1h = sbase + kOffW1h;
+    const uint32_t aW1l = sbase + kOffW1l, aW2h = sbase + kOffW2h, aW2l = sbase + kOffW2l;
+    const uint32_t bar = sbase + kOffBarT + 8 * (uint32_t)(warp_u >> 3);
+    const bool issuer = (warp_u & 7) == 0;          // the first warp of each group issues its MMAs (one elected lane each)
+    uint32_t phase = 0;
+    const int64_t i1 = po.i1;
+    const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
+    // Both groups run the SAME number of tile slots (a slot past the end is all masked rows) so that the epilogue token
+    // below is handed over a matching number of times.
+    const int64_t slots = (tiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
+    // this thread's 8 observation components of one tile, as loaded (split and stored one slot later)
+    float xo[8];
+    auto load_obs = [&](int64_t tile) {
+        const int64_t i = po.i0 + tile * kTile + lt;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = 8 * half + q;
+            xo[q] = (k < kMlpIn && i < i1) ? __ldg(obs + (int64_t)k * n + i) : 0.0f;
+        }
+    };
+    load_obs(2 * (int64_t)blockIdx.x + group);
+    float outv[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // the output layer of the previous tile, written out one slot later
+    int64_t out_i = i1;
+    auto take = [&] { token_take(group); };
+    auto pass = [&] { token_pass(group ^ 1); };
+#if R6_TS_PINGPONG
+    if (group == 1) token_pass(0);           // group 0 takes the first epilogue turn
+#endif
+    for (int64_t slot = 0; slot < slots; slot++) {
+        const int64_t tile = 2 * ((int64_t)blockIdx.x + slot * gridDim.x) + group;
+        const int64_t i = po.i0 + tile * kTile + lt;
+        // ---- observations of this thread's env, split -> row `lt` of the input tile: 8 of its 16 K columns per thread ----
+        {
+            float h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) split_tf32(xo[q], h[q], l[q]);
+            tmem_st8(tmem_row + kColD1 + 8 * half, h);
+            tmem_st8(tmem_row + kColL + 8 * half, l);
+            tmem_st_wait();
+        }
+        fence_before(); group_sync(group);
+        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW0h, aW0l, 512, 2, 128, false); if (elect_one()) mma_commit(bar); }
+        load_obs(tile + 2 * (int64_t)gridDim.x);       // next slot's observations: in flight under this tile's three layers
+        if (half == 0 && out_i < i1) policy_epilogue(po, mlp.log_std, out_i, outv);   // the previous tile's outputs, under MMA0
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
+        epilogue_in_tmem(tmem_row, kColD0, kColL, bias, half, take, pass);
+        fence_before(); group_sync(group);
+        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD1, tmem_g + kColD0, tmem_g + kColL, aW1h, aW1l, 4096, 8, 64, false); if (elect_one()) mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- second half ----
+        epilogue_in_tmem(tmem_row, kColD0 + 64, kColL, bias + 64, half, take, pass);
+        fence_before(); group_sync(group);
+        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD1, tmem_g + kColD0 + 64, tmem_g + kColL, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); if (elect_one()) mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        // ---- hidden layer 1 -> output layer (its 16 accumulator columns reuse the head of the dead D0) ----
+        epilogue_in_tmem(tmem_row, kColD1, kColL, bias + 128, half, take, pass);
+        fence_before(); group_sync(group);
+        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW2h, aW2l, 2048, 8, 16, false); if (elect_one()) mma_commit(bar); }
+        bar_wait(bar, phase); phase ^= 1; fence_after();
+        out_i = i1;
+        if (half == 0) {
+            uint32_t r[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(tmem_row + kColD0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 4; q++) outv[q] = __uint_as_float(r[q]) + bias[192 + q];
+            out_i = i;
+        }
+        // no barrier here: the next slot's input stores go to D1 / L (their reader, this tile's last MMA, has completed),
+        // and the next MMA0, which overwrites the columns just read, is issued behind the group barrier that follows them
+    }
+    if (half == 0 && out_i < i1) policy_epilogue(po, mlp.log_std, out_i, outv);
+#if R6_TS_PINGPONG
+    if (group == 0) token_take(0);           // consume group 1's last hand-over: no barrier is left half-arrived at exit
+#endif
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols3) : "memory");
+}
+
 // GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
 // envs).  HBM-bound: 17 B per (t, env).  No FMA contraction: the float32 roundings are NumPy's.
 __global__ void __launch_bounds__(256)
@@ -1007,6 +1169,7 @@ int ensure_attributes()
     rc |= enable_smem(policy_kernel<false>, kSmemPolicy);
     rc |= enable_smem(policy_tc5_kernel, tc5::kSmemBytes);
     rc |= enable_smem(policy_tc5x3_kernel, tc5x3::kSmemBytes3);
+    rc |= enable_smem(policy_tc5ts_kernel, tc5ts::kSmemBytesT);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -1241,7 +1404,11 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
         if ((reinterpret_cast<uintptr_t>(mlp->w1) & 15u) != 0) return fail(R6_EINVAL, "tensor_cores = 3 needs w1 16-byte aligned%s");
         const int64_t pairs = (blocks_for(count) + 1) / 2;                 // one CTA per SM, two tile groups per CTA
         const unsigned g3 = (unsigned)(pairs < sm_count ? pairs : sm_count);
+#if R6_POLICY_TS
+        policy_tc5ts_kernel<<<g3, tc5x3::kThreads, tc5ts::kSmemBytesT, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+#else
         policy_tc5x3_kernel<<<g3, tc5x3::kThreads, tc5x3::kSmemBytes3, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+#endif
     } else if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);

@@ -221,4 +221,113 @@ __device__ __forceinline__ void issue_mmas3(uint32_t d_tmem, uint32_t ah, uint32
     }
 }
 }  // namespace tc5x3
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same faithful 3xTF32 policy with the ACTIVATIONS IN TENSOR MEMORY (tcgen05.mma with the A operand read from TMEM,
+// only the weights come from shared memory).  Why: with both operands in shared memory an M = 128, N = 64, K = 8 TF32
+// MMA reads 4 KB of A + 2 KB of B for a 32-cycle tensor-pipe slot — 48 cycles of shared-memory bandwidth, and the
+// 3xTF32 chain reads each activation tile twice — so the MMAs of namespace tc5x3 ran at the shared-memory rate, not the
+// tensor-pipe floor, and competed with the epilogue's own stores.  Here an epilogue thread owns TMEM lane = env row:
+// it reads its 32 accumulator columns (tcgen05.ld), applies bias + tanh, splits, and stores hi IN PLACE over the
+// accumulator columns it just read and lo into a 64-column side tile (tcgen05.st) — which is exactly the K-major A
+// layout the MMA wants (row = lane, k = column).  No activation ever touches shared memory, no generic->async proxy
+// fence is needed, and the per-MMA shared-memory read is B only (2 KB at N = 64: under the floor).
+//   TMEM, per group (256 columns):  D0 [0,128)   D1 [128,192)   L [192,256)
+//     layer 0 : A = X   hi D1[0:16)  lo L[0:16)            -> D0[0:128)
+//     layer 1a: A = H0a hi D0[0:64)  (in place) lo L[0:64) -> D1
+//     layer 1b: A = H0b hi D0[64:128)           lo L[0:64) -> D1 +=
+//     layer 2 : A = H1  hi D1[0:64)  (in place) lo L[0:64) -> D0[0:16)   (D0 is dead by then)
+//   shared memory: the split weights (88 KB) + biases + barriers only.
+namespace tc5ts {
+using namespace tc5x3;
+constexpr uint32_t kColL = 192;
+constexpr int kOffBiasT = 88 << 10;
+constexpr int kOffBarT = kOffBiasT + (128 + 64 + 4) * 4;
+constexpr int kOffTmemPtrT = kOffBarT + 16;
+constexpr int kSmemBytesT = kOffTmemPtrT + 16;
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// tanh(D[:, src + 32 half .. + 31] + bias) of this thread's row: hi over the columns just read, lo -> L[32 half ..].
+// `enter` / `leave` bracket the arithmetic only (the XU / FP32 phase two tile groups take turns in); the TMEM load before
+// it and the TMEM stores after it overlap with the other group's turn.
+template <class Enter, class Leave>
+__device__ __forceinline__ void epilogue_in_tmem(uint32_t tmem_row, uint32_t src, uint32_t lo_dst, const float *bias, int half,
+                                                 Enter enter, Leave leave)
+{
+    const int cc = 32 * half;
+    float v[32], l[32];
+    tmem_ld32(tmem_row + src + cc, v);
+    enter();
+#pragma unroll
+    for (int q = 0; q < 32; q++) tc5x3::split_tf32(tc5x3::tanh_f32(v[q] + bias[cc + q]), v[q], l[q]);
+    leave();
+    tmem_st32(tmem_row + src + cc, v);
+    tmem_st32(tmem_row + lo_dst + cc, l);
+    tmem_st_wait();
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+// nk K-blocks of D (+)= (Ah + Al)(Bh + Bl)^T without lo*lo; A tiles are TMEM columns (8 per K-block), B in smem.
+// Called by a whole CONVERGED warp with warp-uniform arguments: the descriptors are then computed on the uniform
+// datapath and each tcgen05.mma is issued by one elected lane straight from uniform registers.  (Issued from a single
+// thread under a divergent branch, every MMA was wrapped in an ELECT / 4 x R2UR / branch "waterfall" of ~75 cycles —
+// three times the 32-cycle tensor-pipe slot of an N = 64 MMA, so the issue rate, not the tensor pipe, set the pace.)
+__device__ __forceinline__ void issue_mmas3_ts(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t b_sbo,
+                                               int nk, int n, bool accumulate_first)
+{
+    const uint32_t idesc = instr_desc(n);
+#pragma unroll
+    for (int kb = 0; kb < nk; kb++) {
+        const uint64_t dbh = smem_desc(bh + kb * 256, 128, b_sbo), dbl = smem_desc(bl + kb * 256, 128, b_sbo);
+        if (elect_one()) {
+            mma_tf32_ts(d_tmem, ah + 8 * kb, dbh, idesc, accumulate_first || kb > 0);
+            mma_tf32_ts(d_tmem, al + 8 * kb, dbh, idesc, true);
+            mma_tf32_ts(d_tmem, ah + 8 * kb, dbl, idesc, true);
+        }
+    }
+}
+}  // namespace tc5ts
 }  // namespace r6
