@@ -257,10 +257,11 @@ int r6_tgo(const double *c2, const double *c3, const double *c4, double c0, int6
  * VecEnv step is then r6_policy followed by r6_step: the network runs as a uniform, high-occupancy GEMM-chain
  * kernel instead of inside the divergent integrator.  obs: float32 [>=13][n] component-major (R6Buffers.obs);
  * actions: float32 [n][3].  tensor_cores = 0: float32 FMAs (R6_ACT_MLP's code); 1: mma.sync TF32 tiles with 3xTF32
- * compensation (|d action| <= 2e-6 vs mode 0); 2: tcgen05.mma kind::tf32 with TMEM accumulators, single pass
- * (fast mode, |d action| ~1e-3 vs mode 0); 3: tcgen05.mma kind::tf32 with 3xTF32 compensation chained into one TMEM
- * accumulator and a float32-accurate tanh (faithful mode, |d action| <= 3e-6 vs mode 0 and vs the reference's
- * recorded actions; the mode the closed-loop and PPO-collection paths use by default).
+ * compensation (|d action| <= 2e-6 vs mode 0); 2: tcgen05.mma kind::tf32 with accumulators and activations in
+ * tensor memory, single pass (fast mode, |d action| ~2e-3 vs mode 0); 3: the same kernel with 3xTF32 compensation
+ * chained into one TMEM accumulator and a float32-accurate tanh (faithful mode, |d action| <= 3e-6 vs mode 0 and vs
+ * the reference's recorded actions; the mode the closed-loop and PPO-collection paths use by default).  Modes 2 and 3
+ * need mlp->w1 16-byte aligned.
  */
 int r6_policy(const R6Mlp *mlp, const float *obs, int64_t n, int32_t tensor_cores, float *actions, void *stream);
 

@@ -8,8 +8,8 @@
 //                                    shared memory) and the uniform reward / flags / reset / observation kernel
 //   step_kernel                      the same step fused (small batches, zero-copy host path)
 //   rollout_kernel, rollout_tc_kernel  k steps per launch with the state in registers (Philox / buffer / policy)
-//   policy_kernel, policy_tc5_kernel   the policy MLP alone: float32 FMAs, mma.sync 3xTF32 tiles, or
-//                                    tcgen05.mma + TMEM (r6_mlp_tc.cuh, r6_mlp_tcgen05.cuh)
+//   policy_kernel, policy_tc5_kernel   the policy MLP alone: float32 FMAs, mma.sync 3xTF32 tiles, or tcgen05.mma with
+//                                    accumulators and activations in TMEM (r6_mlp_tc.cuh, r6_mlp_tcgen05.cuh)
 //   reset_kernel, sim_raw_kernel, tgo_kernel, gae_kernel, peak_fma_kernel
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
@@ -724,106 +724,18 @@ policy_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const P
 constexpr int kSmemPolicyTc = (r6::kMlpTcFloats + (kThreads / 32) * 16 * 33) * (int)sizeof(float);
 constexpr int kSmemPolicy = r6::kMlpFloats * (int)sizeof(float);
 
-// The policy on tcgen05 / TMEM (r6_policy tensor_cores = 2, fast single-pass TF32 mode): see r6_mlp_tcgen05.cuh.
-__global__ void __launch_bounds__(tc5::kTile, 2)
+// The policy on tcgen05 with accumulators and activations in tensor memory (r6_policy tensor_cores = 3: 3xTF32, float32
+// accuracy; tensor_cores = 2: single-pass TF32).  Layout, schedule and measurements: r6_mlp_tcgen05.cuh.
+template <bool kFaithful>
+__global__ void __launch_bounds__(tc5::kThreads, 1)
 policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
 {
     using namespace tc5;
     extern __shared__ __align__(16) double r6_smem[];
     char *S = reinterpret_cast<char *>(r6_smem);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    // ---- one-time per CTA: weights (TF32-rounded) into canonical K-major tiles, biases, barrier, TMEM ----
-    for (int idx = tid; idx < 128 * 16; idx += kTile) {
-        const int r = idx >> 4, k = idx & 15;
-        *reinterpret_cast<float *>(S + kOffW0 + tile_off(r, k, 16)) = k < kMlpIn ? round_tf32(mlp.w0[r * kMlpIn + k]) : 0.0f;
-    }
-    for (int idx = tid; idx < 64 * 128; idx += kTile) {
-        const int r = idx >> 7, k = idx & 127;
-        *reinterpret_cast<float *>(S + kOffW1 + tile_off(r, k, 128)) = round_tf32(mlp.w1[r * kMlpH0 + k]);
-    }
-    for (int idx = tid; idx < 16 * 64; idx += kTile) {
-        const int r = idx >> 6, k = idx & 63;
-        *reinterpret_cast<float *>(S + kOffW2 + tile_off(r, k, 64)) = r < kMlpRows ? round_tf32(mlp_w2_row(mlp, r, k)) : 0.0f;
-    }
-    float *bias = reinterpret_cast<float *>(S + kOffBias);
-    bias[tid] = mlp.b0[tid];
-    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
-    if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
-    const uint32_t bar = smem_u32(S + kOffBar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtr)), "n"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_async_smem();
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtr);
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t aX = smem_u32(S + kOffX), aH = smem_u32(S + kOffH);
-    const uint32_t aW0 = smem_u32(S + kOffW0), aW1 = smem_u32(S + kOffW1), aW2 = smem_u32(S + kOffW2);
-    uint32_t phase = 0;
-    const int64_t i1 = po.i1;
-    const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t i = po.i0 + tile * kTile + tid;
-        // ---- observations of this thread's env -> row `tid` of the X tile ----
-#pragma unroll
-        for (int kc = 0; kc < 4; kc++) {
-            float4 v;
-            v.x = (4 * kc + 0 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 0) * n + i]) : 0.0f;
-            v.y = (4 * kc + 1 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 1) * n + i]) : 0.0f;
-            v.z = (4 * kc + 2 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 2) * n + i]) : 0.0f;
-            v.w = (4 * kc + 3 < kMlpIn && i < i1) ? round_tf32(obs[(int64_t)(4 * kc + 3) * n + i]) : 0.0f;
-            *reinterpret_cast<float4 *>(S + kOffX + tile_off(tid, 4 * kc, 16)) = v;
-        }
-        fence_async_smem(); fence_before(); __syncthreads();
-        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD0, aX, 512, aW0, 512, 2, 128, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
-        epilogue_to_h(tmem_row, kColD0, bias, S + kOffH, tid);
-        fence_async_smem(); fence_before(); __syncthreads();
-        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD1, aH, 2048, aW1, 4096, 8, 64, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- second half ----
-        epilogue_to_h(tmem_row, kColD0 + 64, bias + 64, S + kOffH, tid);
-        fence_async_smem(); fence_before(); __syncthreads();
-        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD1, aH, 2048, aW1 + 2048, 4096, 8, 64, true); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- hidden layer 1 -> output layer ----
-        epilogue_to_h(tmem_row, kColD1, bias + 128, S + kOffH, tid);
-        fence_async_smem(); fence_before(); __syncthreads();
-        if (tid == 0) { fence_after(); issue_mmas(tmem_base + kColD2, aH, 2048, aW2, 2048, 8, 16, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        {
-            float v[32];
-            tmem_ld32(tmem_row + kColD2, v);
-            if (i < i1) {
-                const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
-                policy_epilogue(po, mlp.log_std, i, out);
-            }
-        }
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-}
-
-// The policy on tcgen05 / TMEM at float32 accuracy (r6_policy tensor_cores = 3): 3xTF32-compensated operands, two
-// 128-env tile groups per CTA over one resident copy of the split weights — see r6_mlp_tcgen05.cuh (namespace tc5x3).
-__global__ void __launch_bounds__(tc5x3::kThreads, 1)
-policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
-{
-    using namespace tc5x3;
-    extern __shared__ __align__(16) double r6_smem[];
-    char *S = reinterpret_cast<char *>(r6_smem);
     const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
     // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
-    for (int idx = tid; idx < 128 * 16; idx += tc5x3::kThreads) {
+    for (int idx = tid; idx < 128 * 16; idx += tc5::kThreads) {
         const int r = idx >> 4, k = idx & 15;
         float hi, lo;
         split_tf32(k < kMlpIn ? mlp.w0[r * kMlpIn + k] : 0.0f, hi, lo);
@@ -831,8 +743,8 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
         *reinterpret_cast<float *>(S + kOffW0l + tile_off(r, k, 16)) = lo;
     }
     // W1 / W2 rows are 16-byte aligned runs of 4 consecutive k = one 16-byte chunk of the canonical tile: vector copies
-    // (the staging is a fixed cost per CTA and launch: 11 264 weights; element-wise it was 9 % of the kernel)
-    for (int idx = tid; idx < 64 * 32; idx += tc5x3::kThreads) {
+    // (the staging is a fixed cost per CTA and launch: 11 264 weights)
+    for (int idx = tid; idx < 64 * 32; idx += tc5::kThreads) {
         const int r = idx >> 5, k = (idx & 31) * 4;
         const float4 w = *reinterpret_cast<const float4 *>(mlp.w1 + r * kMlpH0 + k);
         float4 h, l;
@@ -840,7 +752,7 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
         *reinterpret_cast<float4 *>(S + kOffW1h + tile_off(r, k, 128)) = h;
         *reinterpret_cast<float4 *>(S + kOffW1l + tile_off(r, k, 128)) = l;
     }
-    for (int idx = tid; idx < 16 * 16; idx += tc5x3::kThreads) {
+    for (int idx = tid; idx < 16 * 16; idx += tc5::kThreads) {
         const int r = idx >> 4, k = (idx & 15) * 4;
         float4 h, l;
         split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, h.x, l.x);
@@ -850,170 +762,38 @@ policy_tc5x3_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
         *reinterpret_cast<float4 *>(S + kOffW2h + tile_off(r, k, 64)) = h;
         *reinterpret_cast<float4 *>(S + kOffW2l + tile_off(r, k, 64)) = l;
     }
-    float *bias = reinterpret_cast<float *>(S + kOffBias3);
+    float *bias = reinterpret_cast<float *>(S + kOffBias);
     if (tid < 128) bias[tid] = mlp.b0[tid];
     if (tid < 64) bias[128 + tid] = mlp.b1[tid];
     if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar3)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar3 + 8)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar + 8)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtr3)), "n"(kTmemCols3) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtr)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_async_smem();
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtr3);
-    const uint32_t tmem_g = tmem_base + (uint32_t)group * kGroupCols;                      // this group's columns, lane 0
-    const uint32_t tmem_row = tmem_g + ((uint32_t)((warp & 3) * 32) << 16);                // this warp's 32 TMEM lanes
-    char *Hh = S + kOffGroup + group * kGroupBytes, *Hl = Hh + kOffHl;                     // the input tile aliases their heads
-    const uint32_t aHh = smem_u32(Hh), aHl = smem_u32(Hl);
-    const uint32_t aW0h = smem_u32(S + kOffW0h), aW0l = smem_u32(S + kOffW0l), aW1h = smem_u32(S + kOffW1h);
-    const uint32_t aW1l = smem_u32(S + kOffW1l), aW2h = smem_u32(S + kOffW2h), aW2l = smem_u32(S + kOffW2l);
-    const uint32_t bar = smem_u32(S + kOffBar3 + 8 * group);
-    uint32_t phase = 0;
-    const int64_t i1 = po.i1;
-    const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
-    for (int64_t tile = 2 * (int64_t)blockIdx.x + group; tile < tiles; tile += 2 * (int64_t)gridDim.x) {
-        const int64_t i = po.i0 + tile * kTile + lt;
-        // ---- observations of this thread's env, split -> row `lt` of the input tiles (two K-chunks per half) ----
-#pragma unroll
-        for (int kc = 2 * half; kc < 2 * half + 2; kc++) {
-            float4 h, l;
-            split_tf32((4 * kc + 0 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 0) * n + i] : 0.0f, h.x, l.x);
-            split_tf32((4 * kc + 1 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 1) * n + i] : 0.0f, h.y, l.y);
-            split_tf32((4 * kc + 2 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 2) * n + i] : 0.0f, h.z, l.z);
-            split_tf32((4 * kc + 3 < kMlpIn && i < i1) ? obs[(int64_t)(4 * kc + 3) * n + i] : 0.0f, h.w, l.w);
-            *reinterpret_cast<float4 *>(Hh + tile_off(lt, 4 * kc, 16)) = h;
-            *reinterpret_cast<float4 *>(Hl + tile_off(lt, 4 * kc, 16)) = l;
-        }
-        fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD0, aHh, aHl, 512, aW0h, aW0l, 512, 2, 128, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
-        epilogue_to_h3(tmem_row, kColD0, bias, Hh, Hl, lt, half);
-        fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h, aW1l, 4096, 8, 64, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- second half ----
-        epilogue_to_h3(tmem_row, kColD0 + 64, bias + 64, Hh, Hl, lt, half);
-        fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD1, aHh, aHl, 2048, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        // ---- hidden layer 1 -> output layer ----
-        epilogue_to_h3(tmem_row, kColD1, bias + 128, Hh, Hl, lt, half);
-        fence_async_smem(); fence_before(); group_sync(group);
-        if (lt == 0 && half == 0) { fence_after(); issue_mmas3(tmem_g + kColD2, aHh, aHl, 2048, aW2h, aW2l, 2048, 8, 16, false); mma_commit(bar); }
-        bar_wait(bar, phase); phase ^= 1; fence_after();
-        {
-            float v[32];
-            if (half == 0) tmem_ld32(tmem_row + kColD2, v);
-            if (half == 0 && i < i1) {
-                const float out[4] = {v[0] + bias[192], v[1] + bias[193], v[2] + bias[194], v[3] + bias[195]};
-                policy_epilogue(po, mlp.log_std, i, out);
-            }
-        }
-        fence_before(); group_sync(group);       // every warp of the group has read D2 before the next tile's MMAs overwrite D0..D2
-        fence_after();
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols3) : "memory");
-}
-
-// The same policy with the activations kept in tensor memory (A operand of tcgen05.mma read from TMEM; see namespace
-// tc5ts in r6_mlp_tcgen05.cuh): the kernel r6_policy(tensor_cores = 3) launches.
-#ifndef R6_POLICY_TS
-#define R6_POLICY_TS 1
-#endif
-#ifndef R6_TS_PINGPONG
-#define R6_TS_PINGPONG 1
-#endif
-// Epilogue token of the two tile groups (named barriers 3 and 4, 512 participants: the 256 threads of the group that
-// takes the token bar.sync, the 256 of the group that hands it over bar.arrive).  Only one group at a time is in a
-// bias + tanh + split epilogue (the XU / FP32 phase); the other group's MMAs run underneath it.  Without it the two
-// groups fall into lock-step — both in an epilogue fighting for the XU pipe, then both waiting on the tensor pipe.
-__device__ __forceinline__ void token_take(int group)
-{
-#if R6_TS_PINGPONG
-    asm volatile("bar.sync %0, 512;" ::"r"(group + 3) : "memory");
-#endif
-}
-__device__ __forceinline__ void token_pass(int to_group)
-{
-#if R6_TS_PINGPONG
-    asm volatile("bar.arrive %0, 512;" ::"r"(to_group + 3) : "memory");
-#endif
-}
-__global__ void __launch_bounds__(tc5x3::kThreads, 1)
-policy_tc5ts_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, const PolicyOut po)
-{
-    using namespace tc5ts;
-    extern __shared__ __align__(16) double r6_smem[];
-    char *S = reinterpret_cast<char *>(r6_smem);
-    const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
-    // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
-    for (int idx = tid; idx < 128 * 16; idx += tc5x3::kThreads) {
-        const int r = idx >> 4, k = idx & 15;
-        float hi, lo;
-        split_tf32(k < kMlpIn ? mlp.w0[r * kMlpIn + k] : 0.0f, hi, lo);
-        *reinterpret_cast<float *>(S + kOffW0h + tile_off(r, k, 16)) = hi;
-        *reinterpret_cast<float *>(S + kOffW0l + tile_off(r, k, 16)) = lo;
-    }
-    for (int idx = tid; idx < 64 * 32; idx += tc5x3::kThreads) {
-        const int r = idx >> 5, k = (idx & 31) * 4;
-        const float4 w = *reinterpret_cast<const float4 *>(mlp.w1 + r * kMlpH0 + k);
-        float4 h, l;
-        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
-        *reinterpret_cast<float4 *>(S + kOffW1h + tile_off(r, k, 128)) = h;
-        *reinterpret_cast<float4 *>(S + kOffW1l + tile_off(r, k, 128)) = l;
-    }
-    for (int idx = tid; idx < 16 * 16; idx += tc5x3::kThreads) {
-        const int r = idx >> 4, k = (idx & 15) * 4;
-        float4 h, l;
-        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k) : 0.0f, h.x, l.x);
-        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 1) : 0.0f, h.y, l.y);
-        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 2) : 0.0f, h.z, l.z);
-        split_tf32(r < kMlpRows ? mlp_w2_row(mlp, r, k + 3) : 0.0f, h.w, l.w);
-        *reinterpret_cast<float4 *>(S + kOffW2h + tile_off(r, k, 64)) = h;
-        *reinterpret_cast<float4 *>(S + kOffW2l + tile_off(r, k, 64)) = l;
-    }
-    float *bias = reinterpret_cast<float *>(S + kOffBiasT);
-    if (tid < 128) bias[tid] = mlp.b0[tid];
-    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
-    if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBarT)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBarT + 8)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S + kOffTmemPtrT)), "n"(kTmemCols3) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_async_smem();                      // the weight tiles are read by the async proxy (MMA B operand)
+    fence_async_smem();                      // the weight tiles are read by the async proxy (B operand of the MMAs)
     fence_before();
     __syncthreads();
     fence_after();
     // warp-uniform copies (a shuffle result is uniform to the compiler) of everything the MMA-issuing warp computes with
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtrT), 0);
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(S + kOffTmemPtr), 0);
     const uint32_t tmem_g = tmem_base + (uint32_t)(warp_u >> 3) * kGroupCols;              // this group's columns, lane 0
     const uint32_t tmem_row = tmem_g + ((uint32_t)((warp & 3) * 32) << 16);                // this warp's 32 TMEM lanes
     const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(S), 0);
     const uint32_t aW0h = sbase + kOffW0h, aW0l = sbase + kOffW0l, aW1h = sbase + kOffW1h;
     const uint32_t aW1l = sbase + kOffW1l, aW2h = sbase + kOffW2h, aW2l = sbase + kOffW2l;
-    const uint32_t bar = sbase + kOffBarT + 8 * (uint32_t)(warp_u >> 3);
+    const uint32_t bar = sbase + kOffBar + 8 * (uint32_t)(warp_u >> 3);
     const bool issuer = (warp_u & 7) == 0;          // the first warp of each group issues its MMAs (one elected lane each)
     uint32_t phase = 0;
     const int64_t i1 = po.i1;
     const int64_t tiles = (i1 - po.i0 + kTile - 1) / kTile;
     // Both groups run the SAME number of tile slots (a slot past the end is all masked rows) so that the epilogue token
-    // below is handed over a matching number of times.
+    // is handed over a matching number of times.
     const int64_t slots = (tiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
     // this thread's 8 observation components of one tile, as loaded (split and stored one slot later)
     float xo[8];
@@ -1028,11 +808,7 @@ policy_tc5ts_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
     load_obs(2 * (int64_t)blockIdx.x + group);
     float outv[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // the output layer of the previous tile, written out one slot later
     int64_t out_i = i1;
-    auto take = [&] { token_take(group); };
-    auto pass = [&] { token_pass(group ^ 1); };
-#if R6_TS_PINGPONG
-    if (group == 1) token_pass(0);           // group 0 takes the first epilogue turn
-#endif
+    if (group == 1) token_pass(0);                 // group 0 takes the first epilogue turn
     for (int64_t slot = 0; slot < slots; slot++) {
         const int64_t tile = 2 * ((int64_t)blockIdx.x + slot * gridDim.x) + group;
         const int64_t i = po.i0 + tile * kTile + lt;
@@ -1042,49 +818,44 @@ policy_tc5ts_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, c
 #pragma unroll
             for (int q = 0; q < 8; q++) split_tf32(xo[q], h[q], l[q]);
             tmem_st8(tmem_row + kColD1 + 8 * half, h);
-            tmem_st8(tmem_row + kColL + 8 * half, l);
+            if (kFaithful) tmem_st8(tmem_row + kColL + 8 * half, l);
             tmem_st_wait();
         }
         fence_before(); group_sync(group);
-        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW0h, aW0l, 512, 2, 128, false); if (elect_one()) mma_commit(bar); }
+        if (issuer) { fence_after(); issue_mmas<kFaithful>(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW0h, aW0l, 512, 2, 128, false); if (elect_one()) mma_commit(bar); }
         load_obs(tile + 2 * (int64_t)gridDim.x);       // next slot's observations: in flight under this tile's three layers
         if (half == 0 && out_i < i1) policy_epilogue(po, mlp.log_std, out_i, outv);   // the previous tile's outputs, under MMA0
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- hidden layer 0, first half of the units -> layer 1 partial product ----
-        epilogue_in_tmem(tmem_row, kColD0, kColL, bias, half, take, pass);
+        epilogue_in_tmem<kFaithful>(tmem_row, kColD0, bias, half, group);
         fence_before(); group_sync(group);
-        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD1, tmem_g + kColD0, tmem_g + kColL, aW1h, aW1l, 4096, 8, 64, false); if (elect_one()) mma_commit(bar); }
+        if (issuer) { fence_after(); issue_mmas<kFaithful>(tmem_g + kColD1, tmem_g + kColD0, tmem_g + kColL, aW1h, aW1l, 4096, 8, 64, false); if (elect_one()) mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- second half ----
-        epilogue_in_tmem(tmem_row, kColD0 + 64, kColL, bias + 64, half, take, pass);
+        epilogue_in_tmem<kFaithful>(tmem_row, kColD0 + 64, bias + 64, half, group);
         fence_before(); group_sync(group);
-        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD1, tmem_g + kColD0 + 64, tmem_g + kColL, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); if (elect_one()) mma_commit(bar); }
+        if (issuer) { fence_after(); issue_mmas<kFaithful>(tmem_g + kColD1, tmem_g + kColD0 + 64, tmem_g + kColL, aW1h + 2048, aW1l + 2048, 4096, 8, 64, true); if (elect_one()) mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         // ---- hidden layer 1 -> output layer (its 16 accumulator columns reuse the head of the dead D0) ----
-        epilogue_in_tmem(tmem_row, kColD1, kColL, bias + 128, half, take, pass);
+        epilogue_in_tmem<kFaithful>(tmem_row, kColD1, bias + 128, half, group);
         fence_before(); group_sync(group);
-        if (issuer) { fence_after(); issue_mmas3_ts(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW2h, aW2l, 2048, 8, 16, false); if (elect_one()) mma_commit(bar); }
+        if (issuer) { fence_after(); issue_mmas<kFaithful>(tmem_g + kColD0, tmem_g + kColD1, tmem_g + kColL, aW2h, aW2l, 2048, 8, 16, false); if (elect_one()) mma_commit(bar); }
         bar_wait(bar, phase); phase ^= 1; fence_after();
         out_i = i1;
         if (half == 0) {
-            uint32_t r[4];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(tmem_row + kColD0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld4(tmem_row + kColD0, outv);
 #pragma unroll
-            for (int q = 0; q < 4; q++) outv[q] = __uint_as_float(r[q]) + bias[192 + q];
+            for (int q = 0; q < 4; q++) outv[q] += bias[192 + q];
             out_i = i;
         }
         // no barrier here: the next slot's input stores go to D1 / L (their reader, this tile's last MMA, has completed),
         // and the next MMA0, which overwrites the columns just read, is issued behind the group barrier that follows them
     }
     if (half == 0 && out_i < i1) policy_epilogue(po, mlp.log_std, out_i, outv);
-#if R6_TS_PINGPONG
-    if (group == 0) token_take(0);           // consume group 1's last hand-over: no barrier is left half-arrived at exit
-#endif
+    if (group == 0) token_take(0);                 // consume group 1's last hand-over: no barrier is left half-arrived at exit
     fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols3) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
 }
 
 // GAE scan: one thread per env walks its column of the [T][n] trajectory backwards (every access coalesced over
@@ -1167,9 +938,8 @@ int ensure_attributes()
     int rc = enable_all<double>() | enable_all<float>();
     rc |= enable_smem(policy_kernel<true>, kSmemPolicyTc);
     rc |= enable_smem(policy_kernel<false>, kSmemPolicy);
-    rc |= enable_smem(policy_tc5_kernel, tc5::kSmemBytes);
-    rc |= enable_smem(policy_tc5x3_kernel, tc5x3::kSmemBytes3);
-    rc |= enable_smem(policy_tc5ts_kernel, tc5ts::kSmemBytesT);
+    rc |= enable_smem(policy_tc5_kernel<true>, tc5::kSmemBytes);
+    rc |= enable_smem(policy_tc5_kernel<false>, tc5::kSmemBytes);
     rc |= enable_smem(sim_raw_kernel<false>);
     rc |= enable_smem(sim_raw_kernel<true>);
     if (rc) return R6_ECUDA;
@@ -1398,18 +1168,15 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
     const PolicyOut po = {actions, actions_raw, values, log_prob, stochastic, seed, env_offset, step_index, first, first + count};
-    const int64_t wave = (int64_t)sm_count * (tensor_cores == 2 ? 2 : (tensor_cores ? 3 : 4));
+    const int64_t wave = (int64_t)sm_count * (tensor_cores ? 3 : 4);
     const unsigned g = (unsigned)(blocks_for(count) < wave ? blocks_for(count) : wave);
-    if (tensor_cores == 3) {
-        if ((reinterpret_cast<uintptr_t>(mlp->w1) & 15u) != 0) return fail(R6_EINVAL, "tensor_cores = 3 needs w1 16-byte aligned%s");
+    if (tensor_cores >= 2) {
+        if ((reinterpret_cast<uintptr_t>(mlp->w1) & 15u) != 0) return fail(R6_EINVAL, "tensor_cores = 2 / 3 need w1 16-byte aligned%s");
         const int64_t pairs = (blocks_for(count) + 1) / 2;                 // one CTA per SM, two tile groups per CTA
-        const unsigned g3 = (unsigned)(pairs < sm_count ? pairs : sm_count);
-#if R6_POLICY_TS
-        policy_tc5ts_kernel<<<g3, tc5x3::kThreads, tc5ts::kSmemBytesT, (cudaStream_t)stream>>>(*mlp, obs, n, po);
-#else
-        policy_tc5x3_kernel<<<g3, tc5x3::kThreads, tc5x3::kSmemBytes3, (cudaStream_t)stream>>>(*mlp, obs, n, po);
-#endif
-    } else if (tensor_cores == 2) policy_tc5_kernel<<<g, tc5::kTile, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+        const unsigned g5 = (unsigned)(pairs < sm_count ? pairs : sm_count);
+        if (tensor_cores == 3) policy_tc5_kernel<true><<<g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+        else policy_tc5_kernel<false><<<g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+    }
     else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     return check_launch("r6_policy");
