@@ -548,11 +548,11 @@ def run_b200(args):
                                                  "actions": "r6_policy (mma.sync TF32 tiles, 3xTF32) then r6_step"},
         "closed_loop_two_kernels_tcgen05": {"value": world * n * K / (ms_two[2] * 1e-3), "unit": UNIT,
                                             "ms_per_step": ms_two[2] / K, "launches_per_step": 2,
-                                            "actions": "r6_policy (tcgen05.mma kind::tf32, TMEM accumulators, single-pass TF32: "
+                                            "actions": "r6_policy (tcgen05.mma kind::tf32, accumulators and activations in TMEM, single-pass TF32: "
                                                        "|d action| ~1e-3) then r6_step"},
         "closed_loop_two_kernels_tcgen05_3xtf32": {"value": world * n * K / (ms_two[3] * 1e-3), "unit": UNIT,
                                                    "ms_per_step": ms_two[3] / K, "launches_per_step": 2,
-                                                   "actions": "r6_policy (tcgen05.mma kind::tf32, 3xTF32 compensation in one TMEM "
+                                                   "actions": "r6_policy (tcgen05.mma kind::tf32, activations in TMEM, 3xTF32 compensation in one TMEM "
                                                               "accumulator, float32-accurate tanh: |d action| <= 3e-6 vs the "
                                                               "reference's recorded actions) then r6_step — the faithful "
                                                               "closed loop on the 5th-generation tensor cores"},

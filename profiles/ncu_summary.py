@@ -16,7 +16,10 @@ WANT = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occup
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum",
-        "smsp__inst_executed_op_shared_st.sum", "sm__cycles_elapsed.max"]
+        "smsp__inst_executed_op_shared_st.sum", "sm__cycles_elapsed.max",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"]
 
 
 def run(args):
