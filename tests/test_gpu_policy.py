@@ -110,7 +110,7 @@ def test_policy_kernel_and_two_kernel_closed_loop(tensor_cores):
 
 
 def test_tcgen05_policy_fast_mode():
-    """r6_policy tensor_cores = 2 (tcgen05.mma kind::tf32, TMEM accumulators, single pass): its own bound — TF32
+    """r6_policy tensor_cores = 2 (tcgen05.mma kind::tf32, accumulators and activations in TMEM, single pass): its own bound — TF32
     operands carry 2^-11 relative rounding, so actions agree with the float32 network to ~1e-3 (asserted 5e-3),
     ragged batch, and a closed loop driven by it has the same episode statistics to within sampling noise."""
     import torch
@@ -149,7 +149,8 @@ def test_tcgen05_policy_fast_mode():
 
 def test_tcgen05_policy_faithful_mode():
     """r6_policy tensor_cores = 3 (tcgen05.mma kind::tf32 with 3xTF32 error compensation, hi*hi + lo*hi + hi*lo in one TMEM
-    accumulator, two tile groups per CTA): the reference's recorded closed-loop actions at the bar of the float32 FMA
+    accumulator, activations in TMEM, two tile groups per CTA handing an epilogue token back and forth — every batch size
+    below must leave both groups with the same number of hand-overs): the reference's recorded closed-loop actions at the bar of the float32 FMA
     network (3e-6, montecarlo_script.py:57-64 via tests/golden/policy_cl.npz), ragged batches and env sub-ranges, repeated
     launches, and a closed loop with the same episodes as the float32 network."""
     import ctypes as C
@@ -180,6 +181,7 @@ def test_tcgen05_policy_faithful_mode():
         e.obs.copy_(torch.from_numpy(rng.uniform(-1, 1, (14, n)).astype(np.float32)))
         b3, b0 = e.policy_actions(wd, tensor_cores=3), e.policy_actions(wd, tensor_cores=0)
         assert float((b3 - b0).abs().max()) <= 3e-6, n
+        assert float((e.policy_actions(wd, tensor_cores=2) - b0).abs().max()) <= 1e-2, n      # the fast mode of the same kernel
         if n >= 1000:
             m = _lib.make_mlp(wd)
             out = torch.full((n, 3), 7.0, device="cuda")
