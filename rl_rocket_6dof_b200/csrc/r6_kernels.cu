@@ -763,8 +763,9 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, con
         *reinterpret_cast<float4 *>(S + kOffW2l + tile_off(r, k, 64)) = l;
     }
     float *bias = reinterpret_cast<float *>(S + kOffBias);
-    if (tid < 128) bias[tid] = mlp.b0[tid];
-    if (tid < 64) bias[128 + tid] = mlp.b1[tid];
+    const float bscale = kFaithful ? kTwoLog2e : 1.0f;      // faithful mode: hidden-layer biases pre-scaled for the exp2 form of tanh
+    if (tid < 128) bias[tid] = bscale * mlp.b0[tid];
+    if (tid < 64) bias[128 + tid] = bscale * mlp.b1[tid];
     if (tid < 4) bias[192 + tid] = mlp_b2_row(mlp, tid);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S + kOffBar)) : "memory");

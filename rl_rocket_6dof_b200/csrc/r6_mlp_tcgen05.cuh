@@ -177,10 +177,12 @@ __device__ __forceinline__ float tanh_fast(float x)
 }
 // FAITHFUL mode: tanh(x) = 1 - 2 / (exp(2x) + 1) on the exp2 / rcp units: absolute error ~1.5e-7 (the float32 ulp at 1
 // is 6e-8), saturates correctly (exp -> inf => 1, exp -> 0 => -1)
-__device__ __forceinline__ float tanh_exact(float x)
+constexpr float kTwoLog2e = 2.885390081777927f;
+// z = 2 log2(e) x is formed by the caller as fma(acc, kTwoLog2e, kTwoLog2e * bias): one FFMA instead of FADD + FMUL
+__device__ __forceinline__ float tanh_exact_scaled(float z)
 {
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));      // exp(2x) = 2^(2x log2 e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));                           // exp(2x) = 2^(2x log2 e)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
 }
@@ -203,7 +205,7 @@ __device__ __forceinline__ void epilogue_in_tmem(uint32_t tmem_row, uint32_t src
     if constexpr (kFaithful) {
         float l[32];
 #pragma unroll
-        for (int q = 0; q < 32; q++) split_tf32(tanh_exact(v[q] + bias[cc + q]), v[q], l[q]);
+        for (int q = 0; q < 32; q++) split_tf32(tanh_exact_scaled(fmaf(v[q], kTwoLog2e, bias[cc + q])), v[q], l[q]);   // bias pre-scaled
         token_pass(group ^ 1);
         tmem_st32(tmem_row + src + cc, v);
         tmem_st32(tmem_row + kColL + cc, l);
