@@ -323,52 +323,78 @@ class Rocket6DOFBatch:
                         stochastic: bool = True, tensor_cores=3) -> dict:
         """What SB3's `PPO.collect_rollouts` + `RolloutBuffer.compute_returns_and_advantage` produce for k steps of
         this VecEnv, entirely on the device: per step one policy launch (action, value, log-prob; by default the
-        faithful tcgen05 3xTF32 kernel, tensor_cores=3), one env step; then the GAE scan.  Returns tensors shaped [k, N, ...]: obs (13), actions (raw Gaussian samples), values, log_probs,
-        rewards, dones, advantages, returns.  (Bootstrapping time-limit truncations with the critic is left to the
-        caller, as in `gae.compute_gae`.)"""
+        faithful tcgen05 3xTF32 kernel, tensor_cores=3) and one env step, then the GAE scan.  Returns tensors shaped
+        [k, N, ...]: obs (13), actions (raw Gaussian samples), values, log_probs, rewards, dones, advantages, returns.
+        (Bootstrapping time-limit truncations with the critic is left to the caller, as in `gae.compute_gae`.)
+
+        The trajectory is written in place: the env step of step j writes its observations straight into slice j + 1 of
+        a component-major buffer [k + 1, 14, N] (the layout the kernels read and write), its reward and done flags into
+        row j of `rewards` / `dones`, and the policy of step j + 1 reads that slice — no per-step copies (with auto-reset,
+        the training configuration; one-episode batches keep the copies).  `obs` is therefore a strided [k, N, 13] view of
+        that buffer (`.contiguous()` gives dense rows if a consumer needs them)."""
         from .gae import compute_gae
+        k = int(k)
         n, dev = self.num_envs, self.device
-        obs = torch.empty(k, n, 13, dtype=torch.float32, device=dev)
+        self.join()
+        obs_cm = torch.empty(k + 1, 14, n, dtype=torch.float32, device=dev)
+        obs_cm[0].copy_(self.obs)
         acts = torch.empty(k, n, 3, dtype=torch.float32, device=dev)
         vals = torch.empty(k, n, dtype=torch.float32, device=dev)
         logp = torch.empty(k, n, dtype=torch.float32, device=dev)
         rews = torch.empty(k, n, dtype=torch.float32, device=dev)
         dones = torch.empty(k, n, dtype=torch.uint8, device=dev)
         a_env = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        if self.lanes > 1:
-            # every lane records its own rows: [obs copy, policy, env step, reward / done copies] x k on its stream
-            self.join()
-            m = _lib.make_mlp(mlp)
-            L = self.lib
+        m = _lib.make_mlp(mlp)
+        L = self.lib
+        # Without auto-reset a finished env is frozen: the step reads its done flag and writes NOTHING for it, so its
+        # obs / reward / done must carry over from the previous step — that mode keeps the per-step copies.
+        in_place = bool(self.auto_reset)
+        saved = (self._b.obs, self._b.reward_f32, self._b.done)
+        if self.lanes > 1:                           # every lane runs [policy, env step] x k over its env range on its stream
+            jobs = list(enumerate(self._lane_jobs))
             self._lane_fork.record(torch.cuda.current_stream(dev))
             for st in self._lane_streams:
                 st.wait_event(self._lane_fork)
-            for j in range(int(k)):
-                for ln, ((first, count), st) in enumerate(self._lane_jobs):
-                    sl = slice(first, first + count)
-                    with torch.cuda.stream(st):
-                        obs[j, sl] = self.obs[:13, sl].t()
-                        _lib.check(L.r6_policy_range(C.byref(m), self.obs.data_ptr(), n, first, count, int(tensor_cores),
+        else:
+            jobs = [(0, ((0, n), torch.cuda.current_stream(dev)))]
+        try:
+            with torch.cuda.device(dev):
+                for j in range(k):
+                    if in_place:
+                        self._b.obs, self._b.reward_f32, self._b.done = (obs_cm[j + 1].data_ptr(), rews[j].data_ptr(),
+                                                                        dones[j].data_ptr())
+                    for ln, ((first, count), st) in jobs:
+                        if not in_place and j > 0:
+                            with torch.cuda.stream(st):
+                                obs_cm[j, :, first:first + count] = self.obs[:, first:first + count]
+                        _lib.check(L.r6_policy_range(C.byref(m), obs_cm[j].data_ptr(), n, first, count, int(tensor_cores),
                                                      int(bool(stochastic)), self.seed_value, self.env_offset,
                                                      self.steps_done + j, a_env.data_ptr(), acts[j].data_ptr(),
                                                      vals[j].data_ptr(), logp[j].data_ptr(), st.cuda_stream), L)
-                        _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, ln, self.env_offset,
-                                                   a_env.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
-                        rews[j, sl] = self.reward_f32[sl]
-                        dones[j, sl] = self.done[sl]
-            self.steps_done += int(k)
+                        if self.lanes > 1:
+                            _lib.check(L.r6_step_range(C.byref(self._p), C.byref(self._b), n, first, count, ln, self.env_offset,
+                                                       a_env.data_ptr(), self.seed_value, self.steps_done + j, st.cuda_stream), L)
+                        else:                        # whole batch on the caller's stream: r6_step picks fused / split / multi-pass
+                            _lib.check(L.r6_step(C.byref(self._p), C.byref(self._b), n, self.env_offset, a_env.data_ptr(),
+                                                 self.seed_value, st.cuda_stream), L)
+                        if not in_place:
+                            with torch.cuda.stream(st):
+                                rews[j, first:first + count] = self.reward_f32[first:first + count]
+                                dones[j, first:first + count] = self.done[first:first + count]
+        finally:
+            self._b.obs, self._b.reward_f32, self._b.done = saved
+        self.steps_done += k
+        if self.lanes > 1:
             self._lanes_pending = True
             self.join()
-        else:
-            for j in range(int(k)):
-                obs[j] = self.obs[:13].t()
-                self.policy_forward(mlp, stochastic=stochastic, tensor_cores=tensor_cores, out=(a_env, acts[j], vals[j], logp[j]))
-                self.step(a_env)
-                rews[j], dones[j] = self.reward_f32, self.done
+        if k > 0 and in_place:                       # the batch's own output tensors end up as after k calls of step()
+            self.obs.copy_(obs_cm[k])
+            self.reward_f32.copy_(rews[k - 1])
+            self.done.copy_(dones[k - 1])
         _, _, last_v, _ = self.policy_forward(mlp, stochastic=False, tensor_cores=tensor_cores)
         adv, ret = compute_gae(rews, vals, dones, last_v, gamma, gae_lambda)
-        return dict(obs=obs, actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones, advantages=adv,
-                    returns=ret, last_values=last_v)
+        return dict(obs=obs_cm[:k, :13].permute(0, 2, 1), actions=acts, values=vals, log_probs=logp, rewards=rews, dones=dones,
+                    advantages=adv, returns=ret, last_values=last_v)
 
     def step_policy(self, k: int, mlp: dict, *, tensor_cores=3, join: bool = True):
         """k closed-loop env-steps as 2k launches: the policy kernel (a uniform GEMM chain at high occupancy) writes

@@ -395,3 +395,40 @@ def test_collect_rollout_on_device():
                                                         0.99, 0.95)
     assert np.array_equal(adv, ro["advantages"].cpu().numpy()) and np.array_equal(ret, ro["returns"].cpu().numpy())
     assert float(env.stats[7]) == n * k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes,auto_reset", [(1, True), (2, True), (1, False)])
+def test_collect_rollout_in_place_trajectory_equals_step_by_step(lanes, auto_reset):
+    """collect_rollout writes the trajectory in place (the env step's obs / reward / done pointers are redirected into the
+    [k, ...] buffers, the policy reads the previous slice): bit-identical to policy_forward + step + copies per step, on one
+    stream and on two lanes, with and without auto-reset (where the done flags are an INPUT of the step), and the batch's
+    own obs / reward / done tensors end up as after k calls of step()."""
+    import torch
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    w = _actor_critic_weights()
+    wd = {k: torch.from_numpy(v).cuda() for k, v in w.items()}
+    n, k = 3000, (70 if auto_reset else 160)
+    kw = dict(params=env_params(), device="cuda:0", seed=11, auto_reset=auto_reset)
+    a = Rocket6DOFBatch(n, lanes=lanes, **kw)
+    b = Rocket6DOFBatch(n, **kw)
+    a.reset(); b.reset()
+    ro = a.collect_rollout(k, wd, stochastic=True)
+    obs, rew, dn, val, act = [], [], [], [], []
+    for j in range(k):
+        obs.append(b.obs[:13].t().clone())
+        ae, raw, v, lp = b.policy_forward(wd, stochastic=True, tensor_cores=3)
+        b.step(ae)
+        act.append(raw.clone()); val.append(v.clone()); rew.append(b.reward_f32.clone()); dn.append(b.done.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(ro["obs"], torch.stack(obs)) and torch.equal(ro["actions"], torch.stack(act))
+    assert torch.equal(ro["values"], torch.stack(val)) and torch.equal(ro["rewards"], torch.stack(rew))
+    assert torch.equal(ro["dones"], torch.stack(dn))
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.reward_f32, b.reward_f32) and torch.equal(a.done, b.done)
+    assert torch.equal(a.state, b.state) and torch.equal(a.stats, b.stats)
+    if not auto_reset:
+        assert int(dn[-1].sum()) > 0          # some envs did finish and stayed frozen
+    # the batch keeps working normally afterwards (pointers restored)
+    a.step_policy(3, wd); b.step_policy(3, wd)
+    torch.cuda.synchronize()
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.state, b.state)
