@@ -204,6 +204,28 @@ def test_tcgen05_policy_faithful_mode():
     assert abs(stats[0][0]["episodes"] - stats[3][0]["episodes"]) <= 0.002 * stats[0][0]["episodes"] + 2
 
 
+def test_tcgen05_policy_full_size_1m_envs():
+    """The size the closed-loop bench runs at: 2^20 envs whose observations come from 64 closed-loop steps (every phase of
+    an episode present), both tcgen05 modes against the float32 FMA network — 148 CTAs x 2 tile groups x 28 tile slots, the
+    last slot of the second group past the end of the batch."""
+    import torch
+    from rl_rocket_6dof_b200 import policy
+    from rl_rocket_6dof_b200.batch import Rocket6DOFBatch
+    n = (1 << 20) - 77
+    env = Rocket6DOFBatch(n, params=env_params(), device="cuda:0", seed=9)
+    wd = policy.to_device(policy.load_npz(GOLD), env.device)
+    env.reset()
+    env.step_policy(64, wd, tensor_cores=3)
+    a0 = env.policy_actions(wd, tensor_cores=0)
+    a3 = env.policy_actions(wd, tensor_cores=3)
+    a2 = env.policy_actions(wd, tensor_cores=2)
+    torch.cuda.synchronize()
+    d3, d2 = float((a3 - a0).abs().max()), float((a2 - a0).abs().max())
+    print(f"2^20 envs: tcgen05 3xTF32 vs float32 network {d3:.2e}, single-pass TF32 {d2:.2e}")
+    assert d3 <= 3e-6 and d2 <= 1e-2
+    assert bool((a3.abs() <= 1).all()) and bool(torch.isfinite(a3).all())
+
+
 def test_rollout_mlp_needs_weights():
     from rl_rocket_6dof_b200._lib import R6Error
     from rl_rocket_6dof_b200.batch import ACT_MLP, Rocket6DOFBatch
