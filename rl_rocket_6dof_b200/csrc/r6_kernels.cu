@@ -15,6 +15,10 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
 #include <cuda_runtime.h>
 
+#ifndef R6_PDL
+#define R6_PDL 1
+#endif
+
 #include <stdio.h>
 #include <string.h>
 
@@ -97,6 +101,11 @@ __device__ __forceinline__ KStore<R> make_kstore()
 // lane whose episode just ended (about one lane per warp every four steps), straight to L2 — no
 // shuffle tree, no block barrier (warps of a CTA finish their adaptive steps at different times) and
 // no accumulator registers carried through the step.
+// see launch_pdl: returns once the previous grid on the stream has completed and its writes are visible
+// (An explicit early griddepcontrol.launch_dependents was measured too: the dependents' CTAs then sit resident at the wait
+// and take register-file slots from the other lane's running kernel — joined step +1 %.  The implicit trigger at CTA exit
+// keeps only what is free: the next kernel's launch latency under the previous kernel's drain.)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void stats_steps(double *stats, int my_steps)
 {
 
@@ -347,6 +356,7 @@ integrate_first_kernel(const R6Params p, const R6Buffers b, int64_t n, const flo
     K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     PassCtx<R> px;
     bool unfinished = false;
+    grid_dependency_wait();
     if (i < i1 && (p.auto_reset || b.done[i] == 0)) {       // one-episode semantics: finished envs stay frozen
         R *state = reinterpret_cast<R *>(b.state);
         R y[14];
@@ -381,6 +391,7 @@ integrate_resume_kernel(const R6Params p, const R6Buffers b, int64_t n, const fl
     KShared<R, kIntThreads> K;
     K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
     const WorkView W = work_view(b.work, n);
+    grid_dependency_wait();
     const int64_t cnt = W.count[2 * lane + src];
     R *state = reinterpret_cast<R *>(b.state);
     for (int64_t s0 = (int64_t)blockIdx.x * kIntThreads; s0 < cnt; s0 += (int64_t)gridDim.x * kIntThreads) {
@@ -481,6 +492,7 @@ post_kernel(const R6Params p, const R6Buffers b, const Derived dv, int64_t n, in
             const float *__restrict__ actions, uint64_t seed, int64_t step_index, int64_t i0, int64_t i1, int lane)
 {
     const int64_t i = i0 + (int64_t)blockIdx.x * kPostThreads + threadIdx.x;
+    grid_dependency_wait();
     if (b.work != nullptr && blockIdx.x == 0 && threadIdx.x < 2)          // the lane's work lists are consumed: empty them
         reinterpret_cast<int32_t *>(b.work)[2 * lane + threadIdx.x] = 0;
     const bool live = i < i1 && (p.auto_reset || b.done[i] == 0);      // frozen envs (auto_reset = 0, done) are skipped
@@ -969,6 +981,21 @@ int validate_step(const R6Params *p, const R6Buffers *b, int64_t n)
     return R6_OK;
 }
 
+// Programmatic dependent launch (the four kernels of a multi-pass step, back to back on one stream): the next kernel's
+// CTAs may be set up while the previous kernel drains; every such kernel starts with griddepcontrol.wait, which returns
+// once the previous grid has completed and its writes are visible (a no-op for an ordinary launch).
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = R6_PDL;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <class R>
 void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64_t n, int64_t env_offset,
                  const float *actions, uint64_t seed, cudaStream_t s, int64_t step_index = 0, int64_t first = 0,
@@ -983,15 +1010,18 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
         if (b->work != nullptr) {                // integrator cut at attempt boundaries (see integrate_first_kernel)
             // list 0 holds ~2/3 of the range, list 1 ~1 %; the resume kernels walk longer lists with a grid stride
             const unsigned g1 = gi - gi / 4, g2 = gi / 16 + 1;
+            const unsigned gp = (unsigned)((count + kPostThreads - 1) / kPostThreads);
             if (series) {
-                integrate_first_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
-                integrate_resume_kernel<R, false, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
-                integrate_resume_kernel<R, false, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                launch_pdl(integrate_first_kernel<R, false>, gi, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
+                launch_pdl(integrate_resume_kernel<R, false, false>, g1, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                launch_pdl(integrate_resume_kernel<R, false, true>, g2, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, lane);
             } else {
-                integrate_first_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
-                integrate_resume_kernel<R, true, false><<<g1, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
-                integrate_resume_kernel<R, true, true><<<g2, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                launch_pdl(integrate_first_kernel<R, true>, gi, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, last, lane);
+                launch_pdl(integrate_resume_kernel<R, true, false>, g1, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, lane);
+                launch_pdl(integrate_resume_kernel<R, true, true>, g2, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, lane);
             }
+            launch_pdl(post_kernel<R>, gp, kPostThreads, 0, s, *p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
+            return;
         } else if (series)
             integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
         else
