@@ -280,6 +280,7 @@ integrate_kernel(const R6Params p, const R6Buffers b, int64_t n, const float *__
     extern __shared__ __align__(16) double r6_smem[];
     KShared<R, kIntThreads> K;
     K.base = reinterpret_cast<R *>(r6_smem) + 2 * threadIdx.x;
+    grid_dependency_wait();
     if (i >= i1) return;
     if (!p.auto_reset && b.done[i] != 0) return;      // one-episode semantics: a finished env stays frozen until r6_reset
     R *state = reinterpret_cast<R *>(b.state);
@@ -746,6 +747,9 @@ policy_tc5_kernel(const R6Mlp mlp, const float *__restrict__ obs, int64_t n, con
     extern __shared__ __align__(16) double r6_smem[];
     char *S = reinterpret_cast<char *>(r6_smem);
     const int tid = threadIdx.x, group = tid >> 8, lt = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5;
+    // programmatic dependent launch: the previous kernel on the stream may have produced the observations — or the weights
+    // (an optimiser step), so the wait comes before the weight staging, not after it
+    grid_dependency_wait();
     // ---- one-time per CTA: weights split into TF32 hi / lo parts in canonical K-major tiles, biases, barriers, TMEM ----
     for (int idx = tid; idx < 128 * 16; idx += tc5::kThreads) {
         const int r = idx >> 4, k = idx & 15;
@@ -1023,10 +1027,10 @@ void launch_step(const R6Params *p, const R6Buffers *b, const Derived &dv, int64
             launch_pdl(post_kernel<R>, gp, kPostThreads, 0, s, *p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
             return;
         } else if (series)
-            integrate_kernel<R, false><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
+            launch_pdl(integrate_kernel<R, false>, gi, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, last);
         else
-            integrate_kernel<R, true><<<gi, kIntThreads, smem_i, s>>>(*p, *b, n, actions, env_offset, seed, step_index, first, last);
-        post_kernel<R><<<(unsigned)((count + kPostThreads - 1) / kPostThreads), kPostThreads, 0, s>>>(*p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
+            launch_pdl(integrate_kernel<R, true>, gi, kIntThreads, smem_i, s, *p, *b, n, actions, env_offset, seed, step_index, first, last);
+        launch_pdl(post_kernel<R>, (unsigned)((count + kPostThreads - 1) / kPostThreads), kPostThreads, 0, s, *p, *b, dv, n, env_offset, actions, seed, step_index, first, last, lane);
         return;
     }
     const unsigned g = (unsigned)blocks_for(n);
@@ -1205,8 +1209,8 @@ int r6_policy_range(const R6Mlp *mlp, const float *obs, int64_t n, int64_t first
         if ((reinterpret_cast<uintptr_t>(mlp->w1) & 15u) != 0) return fail(R6_EINVAL, "tensor_cores = 2 / 3 need w1 16-byte aligned%s");
         const int64_t pairs = (blocks_for(count) + 1) / 2;                 // one CTA per SM, two tile groups per CTA
         const unsigned g5 = (unsigned)(pairs < sm_count ? pairs : sm_count);
-        if (tensor_cores == 3) policy_tc5_kernel<true><<<g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
-        else policy_tc5_kernel<false><<<g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream>>>(*mlp, obs, n, po);
+        if (tensor_cores == 3) launch_pdl(policy_tc5_kernel<true>, g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream, *mlp, obs, n, po);
+        else launch_pdl(policy_tc5_kernel<false>, g5, tc5::kThreads, tc5::kSmemBytes, (cudaStream_t)stream, *mlp, obs, n, po);
     }
     else if (tensor_cores) policy_kernel<true><<<g, kThreads, kSmemPolicyTc, (cudaStream_t)stream>>>(*mlp, obs, n, po);
     else policy_kernel<false><<<g, kThreads, kSmemPolicy, (cudaStream_t)stream>>>(*mlp, obs, n, po);
